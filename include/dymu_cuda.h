@@ -1,0 +1,237 @@
+/*
+ * dymu_cuda.h -- C ABI of the B200 (sm_100a) device library for DyMu's
+ * total-cost propagation hot path (libdymu_cuda.so).
+ *
+ * The reference (ESA-PRL/planning-path_planning) is a single C++ class with no
+ * FFI of its own; the host-side drop-in class in
+ * planning-path_planning_b200/src/DyMu.hpp keeps that class interface and calls
+ * ONLY the functions below.  Every entry point names the reference code whose
+ * arithmetic it reproduces ("G.cpp" = src/DyMu_GlobalPathPlanning.cpp,
+ * "L.cpp" = src/DyMu_LocalPathRepairing.cpp, "H.hpp" = src/DyMu.hpp).
+ *
+ * Conventions
+ *  - extern "C", opaque context, plain pointers and sizes, no C++/torch types.
+ *  - every call returns DYMU_OK (0) or a negative DYMU_ERR_* code; the text of
+ *    the last error is available from dymu_last_error().  Nothing throws.
+ *  - host matrices are row-major [j][i] with `ld` doubles per row (ld >= nx).
+ *  - all arithmetic is IEEE fp64 without FMA contraction, in the reference's
+ *    expression order.
+ *  - a context is bound to one CUDA device and one stream; not thread-safe
+ *    (the reference class is not either, H.hpp:397-609); use one context per
+ *    GPU / per host thread.
+ *  - there is no CPU fallback: without a CUDA device dymu_create fails.
+ */
+#ifndef DYMU_CUDA_H
+#define DYMU_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dymu_ctx dymu_ctx;
+
+#define DYMU_OK 0
+#define DYMU_ERR_CUDA (-1)      /* a CUDA runtime call failed */
+#define DYMU_ERR_ARG (-2)       /* invalid argument */
+#define DYMU_ERR_STATE (-3)     /* call sequence error (e.g. solve before cost map) */
+#define DYMU_ERR_NOCONV (-4)    /* iteration cap reached before convergence */
+#define DYMU_ERR_CAPACITY (-5)  /* output buffer / local window too small */
+#define DYMU_ERR_NODEVICE (-6)  /* no usable CUDA device */
+
+/* fp64 planes of the global layer (globalNode fields, H.hpp:69-108) */
+#define DYMU_PLANE_ELEVATION 0
+#define DYMU_PLANE_SLOPE 1
+#define DYMU_PLANE_RAW_COST 2
+#define DYMU_PLANE_COST 3
+#define DYMU_PLANE_HAZARD_DENSITY 4
+#define DYMU_PLANE_TRAFFICABILITY 5
+#define DYMU_PLANE_TOTAL_COST 6 /* slot 0; other slots through dymu_download_total_cost */
+#define DYMU_PLANE_CEFF 7       /* global_res*cost*(2+hazard-trafficability), obstacle = +inf */
+/* byte / word planes */
+#define DYMU_PLANE_U8_OBSTACLE 0
+#define DYMU_PLANE_U8_LOCMODE 1 /* index into locomotion_modes, 255 = "DONT_CARE" */
+
+/* read-back transforms */
+#define DYMU_XFORM_NONE 0
+#define DYMU_XFORM_INF_TO_MINUS1 1   /* getTotalCostMatrix, G.cpp:799-811 */
+#define DYMU_XFORM_EFFECTIVE_COST 2  /* getGlobalCostMatrix, G.cpp:815-829 (on DYMU_PLANE_COST) */
+
+typedef struct dymu_solve_stats
+{
+    uint32_t outer_iterations;  /* grid-wide sweep phases of the tile FIM */
+    uint32_t converged;         /* 1 if the active list drained */
+    uint64_t tile_activations;  /* tiles loaded, relaxed in shared memory and stored */
+    uint64_t cell_updates;      /* evaluations of the upwind update (G.cpp:500-546) */
+    uint64_t cells_reached;     /* cells with finite total cost (filled by dymu_count_reached) */
+    float kernel_ms;            /* device time of the solve kernel(s), CUDA events */
+    float reset_ms;             /* device time of the total-cost reset */
+} dymu_solve_stats;
+
+/* ---- context ---------------------------------------------------------- */
+
+/* Global layer allocation.  Replaces initGlobalLayer's per-node `new`
+ * (G.cpp:39-104) with SoA device planes.  device < 0 = current device. */
+int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double local_res,
+                dymu_ctx** out);
+int dymu_destroy(dymu_ctx* ctx);
+const char* dymu_last_error(const dymu_ctx* ctx);
+/* The CUDA stream all work of this context is issued on (cudaStream_t). */
+void* dymu_stream(dymu_ctx* ctx);
+int dymu_synchronize(dymu_ctx* ctx);
+/* Number of kernel launches issued by this context so far. */
+uint64_t dymu_launch_count(const dymu_ctx* ctx);
+/* Device-side timing on the context's stream: record user event `which` (0..7) and read
+ * the elapsed milliseconds between two recorded events (synchronises on event b). */
+int dymu_event_record(dymu_ctx* ctx, int which);
+int dymu_event_elapsed_ms(dymu_ctx* ctx, int a, int b, float* ms);
+/* Tile geometry of the solver: tile edge (cells), padded pitch (doubles per row). */
+int dymu_geometry(const dymu_ctx* ctx, uint32_t* tile, uint32_t* pitch, uint32_t* rows);
+
+/* ---- plane I/O ---------------------------------------------------------- */
+int dymu_upload_plane(dymu_ctx* ctx, int plane, const double* host, size_t ld);
+int dymu_download_plane(dymu_ctx* ctx, int plane, double* host, size_t ld, int xform);
+int dymu_download_plane_u8(dymu_ctx* ctx, int plane, uint8_t* host, size_t ld);
+/* rectangle [i0,i0+w) x [j0,j0+h) of a plane <-> dense host buffer (w*h doubles) */
+int dymu_read_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t w, uint32_t h,
+                   double* host);
+int dymu_write_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t w, uint32_t h,
+                    const double* host);
+int dymu_read_rect_u8(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t w, uint32_t h,
+                      uint8_t* host);
+/* Raw device pointer of a plane (for callers that fill planes on the device). */
+int dymu_plane_device_ptr(dymu_ctx* ctx, int plane, void** dptr, size_t* pitch_elems);
+
+/* ---- cost map ------------------------------------------------------------- */
+/* setCostMap, G.cpp:109-126: cost copy; cost <= 0 => obstacle, trafficability 0,
+ * hazard_density 1.  `host` may be NULL if DYMU_PLANE_COST was already filled. */
+int dymu_set_cost_map(dymu_ctx* ctx, const double* host, size_t ld);
+/* computeCostMap, G.cpp:145-308: slope (G.cpp:186-210), nominal cost from the
+ * [terrain][locomotion][slope] table incl. obstacle marking (G.cpp:217-293),
+ * 5-point smoothing seeded with the previous cost (G.cpp:297-308).
+ * elevation/terrain may be NULL if already resident (terrain plane: see
+ * dymu_upload_terrain). */
+int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, const double* slopes,
+                          int n_slopes, int n_locs, const double* elevation, size_t ld_e,
+                          const double* terrain, size_t ld_t);
+int dymu_upload_terrain(dymu_ctx* ctx, const double* terrain, size_t ld);
+
+/* ---- total-cost solve -------------------------------------------------------- */
+/* Number of independent total-cost planes ("slots") for batched goal queries. */
+int dymu_reserve_slots(dymu_ctx* ctx, uint32_t n_slots);
+/* computeEntireTotalCostMap / computeTotalCostMap, G.cpp:364-568: fixed point of the
+ * first-order upwind update propagateGlobalNode (G.cpp:500-546) with T(goal) = 0, by a
+ * tiled Fast Iterative Method.  n_goals independent problems are solved concurrently,
+ * problem q writing slot q.  `stats` may be NULL or point to n_goals entries
+ * (aggregate numbers are reported in stats[0]). */
+int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_i,
+                          const uint32_t* goal_j, dymu_solve_stats* stats);
+/* Continue a solve after total-cost values were lowered from outside (domain
+ * decomposition halo rows): re-activates the tiles covering rows [j0, j1) of slot 0. */
+int dymu_solve_resume(dymu_ctx* ctx, uint32_t j0, uint32_t j1, dymu_solve_stats* stats);
+int dymu_count_reached(dymu_ctx* ctx, uint32_t slot, uint64_t* n_finite);
+/* CLOSED-set emulation of the early stop in computeTotalCostMap (G.cpp:390): returns
+ * T_stop = max over the start node and its 4 neighbours; cells with T <= T_stop are the
+ * ones the reference would have CLOSED. */
+int dymu_stop_threshold(dymu_ctx* ctx, uint32_t slot, uint32_t start_i, uint32_t start_j,
+                        double* t_stop);
+int dymu_download_total_cost(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform);
+/* values of a plane at n cells (k = j*nx+i), for getTotalCost(Waypoint) G.cpp:860-890 */
+int dymu_read_cells(dymu_ctx* ctx, int plane, uint32_t slot, const uint32_t* cell_index,
+                    uint32_t n, double* out);
+
+/* All fields of one global node in one round trip (globalNode view, H.hpp:69-108):
+ * out[0..9] = elevation, slope, raw_cost, cost, hazard_density, trafficability,
+ * total_cost (slot 0), terrain, isObstacle, locomotion mode index (255 = DONT_CARE). */
+int dymu_read_node(dymu_ctx* ctx, uint32_t i, uint32_t j, double out[10]);
+/* number of cells of a slot with total cost <= threshold (CLOSED-set size) */
+int dymu_count_leq(dymu_ctx* ctx, uint32_t slot, double threshold, uint64_t* n);
+
+/* ---- global path extraction ------------------------------------------------------ */
+#define DYMU_PATH_OK 0
+#define DYMU_PATH_NAN 1        /* first step NaN: G.cpp:628-633 */
+#define DYMU_PATH_STALLED 2    /* step < 0.01*tau*res: G.cpp:650-656 */
+#define DYMU_PATH_CAPACITY 3   /* output buffer exhausted (reference loop is unbounded) */
+#define DYMU_PATH_OUTSIDE 4    /* left the grid (reference would dereference NULL) */
+/* computeGlobalPath, G.cpp:615-714: gradient descent on the device-resident total-cost
+ * plane.  (x0, y0) offset-free metres.  Each output waypoint is 5 doubles
+ * {x, y, z, dCostX, dCostY}: the heading of waypoint k+1 is atan2(-dCostY_k, -dCostX_k)
+ * (G.cpp:709), left to the host so that libm's atan2 is the one used. The goal
+ * waypoint (G.cpp:659-660) is NOT appended. */
+int dymu_extract_global_path(dymu_ctx* ctx, uint32_t slot, double x0, double y0, double tau,
+                             uint32_t goal_i, uint32_t goal_j, double* out, uint32_t cap,
+                             uint32_t* n_out, int* status);
+
+/* ---- local layer --------------------------------------------------------------------- */
+/* The local layer (localNode, H.hpp:42-67) is a dense window of wg x wg global
+ * nodes, r = (uint)(global_res/local_res) local cells per node edge, anchored at
+ * global node (gx0, gy0).  Planes: risk, deviation, local total_cost (fp64),
+ * isObstacle, state (u8). */
+#define DYMU_LPLANE_RISK 0
+#define DYMU_LPLANE_DEVIATION 1
+#define DYMU_LPLANE_TOTAL_COST 2
+#define DYMU_LPLANE_U8_OBSTACLE 0
+#define DYMU_LPLANE_U8_STATE 1
+int dymu_local_create(dymu_ctx* ctx, uint32_t wg);
+int dymu_local_anchor(dymu_ctx* ctx, int64_t gx0, int64_t gy0); /* clears the window */
+int dymu_local_info(const dymu_ctx* ctx, int64_t* gx0, int64_t* gy0, uint32_t* wg, uint32_t* r);
+/* rectangle of the local window in window-local cell coordinates */
+int dymu_local_read_rect(dymu_ctx* ctx, int lplane, uint32_t x0, uint32_t y0, uint32_t w,
+                         uint32_t h, double* host);
+int dymu_local_read_rect_u8(dymu_ctx* ctx, int lplane, uint32_t x0, uint32_t y0, uint32_t w,
+                            uint32_t h, uint8_t* host);
+/* Obstacle ingestion, L.cpp:233-277 (mask part): for every pixel inside the map, the
+ * local cell it falls in (getLocalNode, L.cpp:160-173) becomes an obstacle with risk 1 if
+ * pixel != 0 or the parent global node is an obstacle.  Outputs, in pixel raster order,
+ * the NEW obstacle cells: new_cells[k] = window-local cell index (y*W + x).  The
+ * hazard-density bumps (L.cpp:264-274) and the path-blocking test (L.cpp:441-471)
+ * consume that list. */
+int dymu_local_ingest(dymu_ctx* ctx, const uint8_t* image, uint32_t w, uint32_t h,
+                      uint32_t row_size, uint32_t pixel_size, double res, double rover_x,
+                      double rover_y, uint32_t* new_cells, uint32_t cap, uint32_t* n_new);
+/* isBlockingObstacle over a list of obstacle cells, L.cpp:441-471: returns the
+ * accumulated minIndex / maxIndex and whether any obstacle blocks the path. */
+int dymu_local_blocking(dymu_ctx* ctx, const uint32_t* cells, uint32_t n_cells,
+                        const double* path_xy, uint32_t n_path, double risk_distance,
+                        uint32_t* min_index, uint32_t* max_index, int* blocked);
+/* expandRisk, L.cpp:493-576: fixed point of propagateRisk from all obstacle cells. */
+int dymu_local_expand_risk(dymu_ctx* ctx, double risk_distance, dymu_solve_stats* stats);
+/* computeLocalPropagation, L.cpp:578-805: narrow-band march on `deviation` in the
+ * reference's exact pop order (vector position tie-break included).
+ * approach: 0 CONSERVATIVE (end node given), 1 SWEEPING (end node discovered).
+ * Returns end cell (window-local index) or -1 when the reference returns NULL. */
+int dymu_local_propagate(dymu_ctx* ctx, int approach, double start_x, double start_y,
+                         double overtake_x, double overtake_y, double t_overtake,
+                         double risk_ratio, int64_t* end_cell, uint32_t* status,
+                         uint64_t* n_closed);
+#define DYMU_LOCAL_OK 0
+#define DYMU_LOCAL_START_IN_OBSTACLE 1
+#define DYMU_LOCAL_END_IN_OBSTACLE 2
+#define DYMU_LOCAL_EXHAUSTED 3      /* narrow band drained (reference: watchdog / crash) */
+#define DYMU_LOCAL_WINDOW_EXCEEDED 4 /* the wave reached the window border */
+/* getLocalPath, L.cpp:807-1023.  Output waypoints {x, y, z, dCostX, dCostY, kind}:
+ * kind 0 = gradient step (heading atan2(dCostY,dCostX), L.cpp:974), 1 = Dijkstra
+ * fallback step (heading atan2(dCostY,dCostX) with the stored deltas, L.cpp:866-867),
+ * 2 = first waypoint whose gradient step was rejected (heading of the end node, L.cpp:815).
+ * (offset_x, offset_y) = global_offset, subtracted once more for the elevation look-up
+ * exactly as L.cpp:890-891 does.
+ * Stored in the order the reference inserts them (last inserted = front). */
+int dymu_local_extract_path(dymu_ctx* ctx, int64_t end_cell, double start_x, double start_y,
+                            double offset_x, double offset_y, double* out, uint32_t cap,
+                            uint32_t* n_out, int* status);
+/* per window global node (wg*wg bytes, row-major): 1 if the last propagation looked into a
+ * local node of that global node from a different parent, i.e. the reference would have
+ * called subdivideGlobalNode on it (L.cpp:658-663).  clear != 0 resets the flags. */
+int dymu_local_read_entered(dymu_ctx* ctx, uint8_t* host, int clear);
+/* risk at the local cells containing n waypoints (evaluatePath, L.cpp:1046-1047);
+ * cells outside the window report 0. */
+int dymu_local_sample_risk(dymu_ctx* ctx, const double* xy, uint32_t n, double* risk_out);
+/* world->window mapping of getLocalNode (L.cpp:160-189); -1 if outside the window */
+int dymu_local_cell_of(dymu_ctx* ctx, double x, double y, int64_t* cell);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYMU_CUDA_H */

@@ -1,0 +1,383 @@
+"""ctypes binding of include/dymu_cuda.h (libdymu_cuda.so).
+
+Thin and explicit: one Python method per C entry point, numpy arrays in and out.
+There is no CPU fallback; ``DeviceLayer`` raises if the library is missing or no
+CUDA device can be opened.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_SO = os.path.join(HERE, "libdymu_cuda.so")
+
+OK = 0
+PLANE = {"elevation": 0, "slope": 1, "raw_cost": 2, "cost": 3, "hazard_density": 4,
+         "trafficability": 5, "total_cost": 6, "ceff": 7}
+PLANE_U8 = {"obstacle": 0, "locmode": 1}
+XFORM_NONE, XFORM_INF_TO_MINUS1, XFORM_EFFECTIVE_COST = 0, 1, 2
+LPLANE = {"risk": 0, "deviation": 1, "total_cost": 2}
+LPLANE_U8 = {"obstacle": 0, "state": 1}
+
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("outer_iterations", C.c_uint32), ("converged", C.c_uint32),
+                ("tile_activations", C.c_uint64), ("cell_updates", C.c_uint64),
+                ("cells_reached", C.c_uint64), ("kernel_ms", C.c_float), ("reset_ms", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_SIG = {
+    "dymu_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_double,
+                              C.POINTER(C.c_void_p)]),
+    "dymu_destroy": (C.c_int, [C.c_void_p]),
+    "dymu_last_error": (C.c_char_p, [C.c_void_p]),
+    "dymu_stream": (C.c_void_p, [C.c_void_p]),
+    "dymu_synchronize": (C.c_int, [C.c_void_p]),
+    "dymu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "dymu_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "dymu_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "dymu_geometry": (C.c_int, [C.c_void_p, _u32p, _u32p, _u32p]),
+    "dymu_upload_plane": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t]),
+    "dymu_download_plane": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t, C.c_int]),
+    "dymu_download_plane_u8": (C.c_int, [C.c_void_p, C.c_int, _u8p, C.c_size_t]),
+    "dymu_read_rect": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.c_uint32, _dp]),
+    "dymu_write_rect": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.c_uint32, _dp]),
+    "dymu_read_rect_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_uint32, _u8p]),
+    "dymu_plane_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_size_t)]),
+    "dymu_set_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_size_t]),
+    "dymu_compute_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp,
+                                        C.c_size_t, _dp, C.c_size_t]),
+    "dymu_upload_terrain": (C.c_int, [C.c_void_p, _dp, C.c_size_t]),
+    "dymu_reserve_slots": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "dymu_solve_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p,
+                                        C.POINTER(SolveStats)]),
+    "dymu_solve_resume": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SolveStats)]),
+    "dymu_count_reached": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "dymu_stop_threshold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp]),
+    "dymu_download_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_size_t, C.c_int]),
+    "dymu_read_cells": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, _u32p, C.c_uint32, _dp]),
+    "dymu_read_node": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _dp]),
+    "dymu_count_leq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.POINTER(C.c_uint64)]),
+    "dymu_extract_global_path": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_double,
+                                           C.c_double, C.c_uint32, C.c_uint32, _dp, C.c_uint32,
+                                           _u32p, C.POINTER(C.c_int)]),
+    "dymu_local_create": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "dymu_local_anchor": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "dymu_local_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _u32p,
+                                  _u32p]),
+    "dymu_local_read_rect": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, _dp]),
+    "dymu_local_read_rect_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, _u8p]),
+    "dymu_local_ingest": (C.c_int, [C.c_void_p, _u8p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_uint32, C.c_double, C.c_double, C.c_double, _u32p,
+                                    C.c_uint32, _u32p]),
+    "dymu_local_blocking": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, _dp, C.c_uint32, C.c_double,
+                                      _u32p, _u32p, C.POINTER(C.c_int)]),
+    "dymu_local_expand_risk": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(SolveStats)]),
+    "dymu_local_propagate": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int64),
+                                       _u32p, C.POINTER(C.c_uint64)]),
+    "dymu_local_extract_path": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                          C.c_double, C.c_double, _dp, C.c_uint32, _u32p,
+                                          C.POINTER(C.c_int)]),
+    "dymu_local_read_entered": (C.c_int, [C.c_void_p, _u8p, C.c_int]),
+    "dymu_local_sample_risk": (C.c_int, [C.c_void_p, _dp, C.c_uint32, _dp]),
+    "dymu_local_cell_of": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_int64)]),
+}
+
+CUDA_SYMBOLS = tuple(_SIG)
+_LIB = None
+
+
+def load_library():
+    """Loads libdymu_cuda.so (RTLD_GLOBAL so libdymu_b200.so resolves against it)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(CUDA_SO):
+            raise RuntimeError("libdymu_cuda.so is not built: run "
+                               "`python planning-path_planning_b200/build.py` (no CPU fallback)")
+        lib = C.CDLL(CUDA_SO, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIG.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = lib
+    return _LIB
+
+
+class DymuError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("dymu_cuda error %d: %s" % (code, text))
+        self.code = code
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class DeviceLayer:
+    """One dymu_ctx: the global layer of a DyMu planner resident on one GPU."""
+
+    def __init__(self, nx, ny, global_res=1.0, local_res=0.1, device=-1):
+        self._l = load_library()
+        self._h = C.c_void_p()
+        self.nx, self.ny = int(nx), int(ny)
+        rc = self._l.dymu_create(device, self.nx, self.ny, global_res, local_res,
+                                 C.byref(self._h))
+        if rc != OK:
+            text = self._l.dymu_last_error(self._h).decode() if self._h else "no CUDA device"
+            if self._h:
+                self._l.dymu_destroy(self._h)
+                self._h = C.c_void_p()
+            raise DymuError(rc, text)
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise DymuError(rc, self._l.dymu_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._l.dymu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # context
+    @property
+    def stream(self):
+        return self._l.dymu_stream(self._h)
+
+    def synchronize(self):
+        self._chk(self._l.dymu_synchronize(self._h))
+
+    @property
+    def launches(self):
+        return int(self._l.dymu_launch_count(self._h))
+
+    def event_record(self, which):
+        self._chk(self._l.dymu_event_record(self._h, which))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._chk(self._l.dymu_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def geometry(self):
+        t, p, r = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._chk(self._l.dymu_geometry(self._h, C.byref(t), C.byref(p), C.byref(r)))
+        return t.value, p.value, r.value
+
+    # planes
+    def upload_plane(self, name, host):
+        a = _f64(host)
+        self._chk(self._l.dymu_upload_plane(self._h, PLANE[name], a.ctypes.data_as(_dp),
+                                            a.shape[1]))
+
+    def download_plane(self, name, xform=XFORM_NONE, out=None):
+        if out is None:
+            out = np.empty((self.ny, self.nx), dtype=np.float64)
+        self._chk(self._l.dymu_download_plane(self._h, PLANE[name], out.ctypes.data_as(_dp),
+                                              out.shape[1], xform))
+        return out
+
+    def download_plane_u8(self, name):
+        out = np.empty((self.ny, self.nx), dtype=np.uint8)
+        self._chk(self._l.dymu_download_plane_u8(self._h, PLANE_U8[name],
+                                                 out.ctypes.data_as(_u8p), self.nx))
+        return out
+
+    def read_rect(self, name, i0, j0, w, h):
+        out = np.empty((h, w), dtype=np.float64)
+        self._chk(self._l.dymu_read_rect(self._h, PLANE[name], i0, j0, w, h,
+                                         out.ctypes.data_as(_dp)))
+        return out
+
+    def write_rect(self, name, i0, j0, values):
+        a = _f64(values)
+        self._chk(self._l.dymu_write_rect(self._h, PLANE[name], i0, j0, a.shape[1], a.shape[0],
+                                          a.ctypes.data_as(_dp)))
+
+    def plane_device_ptr(self, name):
+        p, pitch = C.c_void_p(), C.c_size_t()
+        self._chk(self._l.dymu_plane_device_ptr(self._h, PLANE[name], C.byref(p), C.byref(pitch)))
+        return p.value, pitch.value
+
+    # cost map
+    def set_cost_map(self, cost=None):
+        if cost is None:
+            self._chk(self._l.dymu_set_cost_map(self._h, None, 0))
+        else:
+            a = _f64(cost)
+            self._chk(self._l.dymu_set_cost_map(self._h, a.ctypes.data_as(_dp), a.shape[1]))
+
+    def compute_cost_map(self, lut, slopes, n_locs, elevation=None, terrain=None):
+        lut, slopes = _f64(lut), _f64(slopes)
+        e = _f64(elevation) if elevation is not None else None
+        t = _f64(terrain) if terrain is not None else None
+        self._chk(self._l.dymu_compute_cost_map(
+            self._h, lut.ctypes.data_as(_dp), lut.size, slopes.ctypes.data_as(_dp), slopes.size,
+            n_locs, e.ctypes.data_as(_dp) if e is not None else None,
+            e.shape[1] if e is not None else 0,
+            t.ctypes.data_as(_dp) if t is not None else None, t.shape[1] if t is not None else 0))
+
+    # solve
+    def reserve_slots(self, n):
+        self._chk(self._l.dymu_reserve_slots(self._h, n))
+
+    def solve_total_cost(self, goals):
+        """goals: iterable of (i, j).  Returns the aggregate SolveStats as a dict."""
+        g = np.asarray(list(goals), dtype=np.uint32).reshape(-1, 2)
+        gi, gj = np.ascontiguousarray(g[:, 0]), np.ascontiguousarray(g[:, 1])
+        st = SolveStats()
+        self._chk(self._l.dymu_solve_total_cost(self._h, g.shape[0], gi.ctypes.data_as(_u32p),
+                                                gj.ctypes.data_as(_u32p), C.byref(st)))
+        return st.as_dict()
+
+    def solve_resume(self, j0, j1):
+        st = SolveStats()
+        self._chk(self._l.dymu_solve_resume(self._h, j0, j1, C.byref(st)))
+        return st.as_dict()
+
+    def count_reached(self, slot=0):
+        n = C.c_uint64()
+        self._chk(self._l.dymu_count_reached(self._h, slot, C.byref(n)))
+        return int(n.value)
+
+    def read_node(self, i, j):
+        out = np.empty(10, dtype=np.float64)
+        self._chk(self._l.dymu_read_node(self._h, i, j, out.ctypes.data_as(_dp)))
+        return out
+
+    def count_leq(self, threshold, slot=0):
+        n = C.c_uint64()
+        self._chk(self._l.dymu_count_leq(self._h, slot, threshold, C.byref(n)))
+        return int(n.value)
+
+    def stop_threshold(self, start_i, start_j, slot=0):
+        t = C.c_double()
+        self._chk(self._l.dymu_stop_threshold(self._h, slot, start_i, start_j, C.byref(t)))
+        return t.value
+
+    def download_total_cost(self, slot=0, xform=XFORM_NONE, out=None):
+        if out is None:
+            out = np.empty((self.ny, self.nx), dtype=np.float64)
+        self._chk(self._l.dymu_download_total_cost(self._h, slot, out.ctypes.data_as(_dp),
+                                                   out.shape[1], xform))
+        return out
+
+    def read_cells(self, name, cells, slot=0):
+        idx = np.ascontiguousarray(cells, dtype=np.uint32)
+        out = np.empty(idx.size, dtype=np.float64)
+        self._chk(self._l.dymu_read_cells(self._h, PLANE[name], slot, idx.ctypes.data_as(_u32p),
+                                          idx.size, out.ctypes.data_as(_dp)))
+        return out
+
+    def extract_global_path(self, x0, y0, tau, goal_i, goal_j, slot=0, cap=1 << 18):
+        """Returns ((n,5) array of x, y, z, dCostX, dCostY, status)."""
+        out = np.empty((cap, 5), dtype=np.float64)
+        n, status = C.c_uint32(), C.c_int()
+        self._chk(self._l.dymu_extract_global_path(self._h, slot, x0, y0, tau, goal_i, goal_j,
+                                                   out.ctypes.data_as(_dp), cap, C.byref(n),
+                                                   C.byref(status)))
+        return out[:n.value].copy(), status.value
+
+    # local layer
+    def local_create(self, wg):
+        self._chk(self._l.dymu_local_create(self._h, wg))
+
+    def local_anchor(self, gx0, gy0):
+        self._chk(self._l.dymu_local_anchor(self._h, gx0, gy0))
+
+    def local_info(self):
+        gx0, gy0, wg, r = C.c_int64(), C.c_int64(), C.c_uint32(), C.c_uint32()
+        self._chk(self._l.dymu_local_info(self._h, C.byref(gx0), C.byref(gy0), C.byref(wg),
+                                          C.byref(r)))
+        return gx0.value, gy0.value, wg.value, r.value
+
+    def local_read(self, name, x0=0, y0=0, w=None, h=None):
+        _, _, wg, r = self.local_info()
+        w = wg * r - x0 if w is None else w
+        h = wg * r - y0 if h is None else h
+        if name in LPLANE:
+            out = np.empty((h, w), dtype=np.float64)
+            self._chk(self._l.dymu_local_read_rect(self._h, LPLANE[name], x0, y0, w, h,
+                                                   out.ctypes.data_as(_dp)))
+        else:
+            key = {"isObstacle": "obstacle"}.get(name, name)
+            out = np.empty((h, w), dtype=np.uint8)
+            self._chk(self._l.dymu_local_read_rect_u8(self._h, LPLANE_U8[key], x0, y0, w, h,
+                                                      out.ctypes.data_as(_u8p)))
+        return out
+
+    def local_ingest(self, image, res, rover_x, rover_y):
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        h, w = img.shape
+        cap = w * h
+        cells = np.empty(cap, dtype=np.uint32)
+        n = C.c_uint32()
+        self._chk(self._l.dymu_local_ingest(self._h, img.ctypes.data_as(_u8p), w, h, w, 1, res,
+                                            rover_x, rover_y, cells.ctypes.data_as(_u32p), cap,
+                                            C.byref(n)))
+        return cells[:n.value].copy()
+
+    def local_blocking(self, cells, path_xy, risk_distance, min_index, max_index):
+        c = np.ascontiguousarray(cells, dtype=np.uint32)
+        p = _f64(path_xy)
+        mn, mx, b = C.c_uint32(min_index), C.c_uint32(max_index), C.c_int()
+        self._chk(self._l.dymu_local_blocking(self._h, c.ctypes.data_as(_u32p), c.size,
+                                              p.ctypes.data_as(_dp), p.shape[0], risk_distance,
+                                              C.byref(mn), C.byref(mx), C.byref(b)))
+        return mn.value, mx.value, bool(b.value)
+
+    def local_expand_risk(self, risk_distance):
+        st = SolveStats()
+        self._chk(self._l.dymu_local_expand_risk(self._h, risk_distance, C.byref(st)))
+        return st.as_dict()
+
+    def local_propagate(self, approach, start, overtake, t_overtake, risk_ratio):
+        end, status, closed = C.c_int64(), C.c_uint32(), C.c_uint64()
+        self._chk(self._l.dymu_local_propagate(self._h, approach, start[0], start[1], overtake[0],
+                                               overtake[1], t_overtake, risk_ratio, C.byref(end),
+                                               C.byref(status), C.byref(closed)))
+        return end.value, status.value, closed.value
+
+    def local_extract_path(self, end_cell, start, offset=(0.0, 0.0), cap=1 << 16):
+        out = np.empty((cap, 6), dtype=np.float64)
+        n, status = C.c_uint32(), C.c_int()
+        self._chk(self._l.dymu_local_extract_path(self._h, end_cell, start[0], start[1], offset[0],
+                                                  offset[1], out.ctypes.data_as(_dp), cap,
+                                                  C.byref(n), C.byref(status)))
+        return out[:n.value].copy(), status.value
+
+    def local_read_entered(self, clear=False):
+        _, _, wg, _ = self.local_info()
+        out = np.empty((wg, wg), dtype=np.uint8)
+        self._chk(self._l.dymu_local_read_entered(self._h, out.ctypes.data_as(_u8p), int(clear)))
+        return out
+
+    def local_sample_risk(self, xy):
+        a = _f64(xy)
+        out = np.empty(a.shape[0], dtype=np.float64)
+        self._chk(self._l.dymu_local_sample_risk(self._h, a.ctypes.data_as(_dp), a.shape[0],
+                                                 out.ctypes.data_as(_dp)))
+        return out
+
+    def local_cell_of(self, x, y):
+        c = C.c_int64()
+        self._chk(self._l.dymu_local_cell_of(self._h, x, y, C.byref(c)))
+        return c.value

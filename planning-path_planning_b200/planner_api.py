@@ -1,9 +1,8 @@
 """ctypes view of include/dymu_planner_c.h.
 
-The same class drives either shared library that implements that header:
-``oracle/_ref/libdymu_ref.so`` (the unmodified reference, test oracle) or
+The same class drives any shared library that implements that header:
 ``libdymu_b200.so`` (this repository's drop-in DyMuPathPlanner on top of the
-CUDA C-ABI).  Method names mirror the reference class
+CUDA C-ABI) or, in the test-suite only, the compiled unmodified reference.  Method names mirror the reference class
 (``/root/reference/src/DyMu.hpp:471-608``) so that parity tests read like
 calls on ``PathPlanning_lib::DyMuPathPlanner``.
 """

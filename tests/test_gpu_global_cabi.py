@@ -1,0 +1,104 @@
+"""GPU parity of the global layer through the device C ABI (include/dymu_cuda.h) against the
+CPU oracle: cost-map stencils bit-exact, total-cost map <= 1e-9 relative (north_star bound;
+observed ~1e-15), identical unreachable mask, waypoints <= 1e-3 cell."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_T = 1e-9      # relative, total-cost map (BASELINE.json north_star)
+TOL_WP = 1e-3     # cells, waypoint positions
+
+
+def _mars(pkg, oracle_mod, ny, nx, seed):
+    syn = pkg.synthetic
+    elev, terr = syn.mars_dem(ny, nx, seed=seed)
+    lut, slopes, locs = syn.default_lut()
+    po = oracle_mod.Port(1.0, 1.5, 2.0, oracle_mod.SWEEPING)
+    po.initGlobalLayer(1.0, 0.1, nx, ny)
+    assert po.computeCostMap(lut, slopes, locs, elev, terr)
+    dev = pkg.cuda_api.DeviceLayer(nx, ny, 1.0, 0.1)
+    dev.compute_cost_map(lut, slopes, len(locs), elev, terr)
+    return po, dev
+
+
+@pytest.mark.parametrize("ny,nx,seed", [(100, 100, 1), (129, 257, 2), (300, 300, 3), (64, 64, 4)])
+def test_cost_map_stencils_bit_exact(pkg, oracle_mod, ny, nx, seed):
+    po, dev = _mars(pkg, oracle_mod, ny, nx, seed)
+    assert np.array_equal(dev.download_plane_u8("obstacle"), po.plane("isObstacle"))
+    for name in ("slope", "raw_cost", "cost", "hazard_density", "trafficability"):
+        a, b = dev.download_plane(name), po.plane(name)
+        assert rel_err(a, b) <= 1e-14, name
+    # second call exercises the smoothing quirk (seeded with the previous cost, G.cpp:299)
+    syn = pkg.synthetic
+    elev, terr = syn.mars_dem(ny, nx, seed=seed)
+    lut, slopes, locs = syn.default_lut()
+    po.computeCostMap(lut, slopes, locs, elev, terr)
+    dev.compute_cost_map(lut, slopes, len(locs), elev, terr)
+    assert rel_err(dev.download_plane("cost"), po.plane("cost")) <= 1e-14
+
+
+@pytest.mark.parametrize("ny,nx,seed", [(100, 100, 1), (129, 257, 2), (300, 300, 3), (64, 64, 4),
+                                        (33, 95, 5)])
+def test_total_cost_map_matches_oracle(pkg, oracle_mod, ny, nx, seed):
+    po, dev = _mars(pkg, oracle_mod, ny, nx, seed)
+    ob = po.plane("isObstacle")
+    gi, gj = pkg.synthetic.free_interior_cell_near(ob, nx // 2, ny // 2)
+    assert po.setGoal(gi, gj) and po.computeEntireTotalCostMap()
+    stats = dev.solve_total_cost([(gi, gj)])
+    assert stats["converged"] == 1
+    T = dev.download_total_cost()
+    To = po.plane("total_cost")
+    assert np.array_equal(np.isinf(T), np.isinf(To)), "unreachable mask differs"
+    assert rel_err(T, To) <= TOL_T
+    Tm = dev.download_total_cost(xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
+    assert np.array_equal(Tm < 0, np.isinf(To))
+    assert po.fixed_point_violations(T, 1e-12) == 0
+    assert dev.count_reached() == int(np.isfinite(To).sum())
+
+
+def test_set_cost_map_variant_and_path(pkg, oracle_mod):
+    nx = ny = 200
+    cost = pkg.synthetic.smooth_cost_map(ny, nx, seed=9)
+    po = oracle_mod.Port(1.0, 1.5, 2.0, oracle_mod.SWEEPING)
+    po.initGlobalLayer(1.0, 0.1, nx, ny)
+    po.setCostMap(cost)
+    dev = pkg.cuda_api.DeviceLayer(nx, ny, 1.0, 0.1)
+    dev.set_cost_map(cost)
+    ob = po.plane("isObstacle")
+    assert np.array_equal(dev.download_plane_u8("obstacle"), ob)
+    gi, gj = pkg.synthetic.free_interior_cell_near(ob, 160, 160)
+    si, sj = pkg.synthetic.free_interior_cell_near(ob, 40, 40)
+    po.setGoal(gi, gj)
+    po.computeEntireTotalCostMap()
+    dev.solve_total_cost([(gi, gj)])
+    assert rel_err(dev.download_total_cost(), po.plane("total_cost")) <= TOL_T
+    assert po.computeGlobalPath(float(si), float(sj)) == 1
+    ref_path = po.current_path
+    wps, status = dev.extract_global_path(float(si), float(sj), 0.4, gi, gj)
+    assert status == 0
+    assert wps.shape[0] == ref_path.shape[0] - 1  # goal waypoint is appended by the host
+    assert np.max(np.abs(wps[:, :2] - ref_path[:-1, :2])) <= TOL_WP
+    head = np.arctan2(-wps[:-1, 4], -wps[:-1, 3])
+    assert np.max(np.abs(head - ref_path[1:-1, 3])) <= 1e-6
+
+
+def test_batched_goals_share_one_launch(pkg, oracle_mod):
+    nx = ny = 160
+    cost = pkg.synthetic.smooth_cost_map(ny, nx, seed=11)
+    dev = pkg.cuda_api.DeviceLayer(nx, ny, 1.0, 0.1)
+    dev.set_cost_map(cost)
+    dev.reserve_slots(4)
+    ob = dev.download_plane_u8("obstacle")
+    goals = [pkg.synthetic.free_interior_cell_near(ob, x, y) for x, y in
+             ((30, 30), (120, 40), (80, 80), (40, 130))]
+    dev.solve_total_cost(goals)
+    for q, (gi, gj) in enumerate(goals):
+        po = oracle_mod.Port(1.0, 1.5, 2.0, 1)
+        po.initGlobalLayer(1.0, 0.1, nx, ny)
+        po.setCostMap(cost)
+        po.setGoal(gi, gj)
+        po.computeEntireTotalCostMap(heap=True)
+        assert rel_err(dev.download_total_cost(slot=q), po.plane("total_cost")) <= TOL_T

