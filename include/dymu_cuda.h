@@ -66,6 +66,8 @@ typedef struct dymu_solve_stats
     uint64_t tile_activations;  /* tiles loaded, relaxed in shared memory and stored */
     uint64_t cell_updates;      /* evaluations of the upwind update (G.cpp:500-546) */
     uint64_t cells_reached;     /* cells with finite total cost (filled by dymu_count_reached) */
+    uint64_t tiles_deferred;    /* list entries carried over by the priority band */
+    uint64_t inner_iterations;  /* shared-memory sweeps summed over tile activations */
     float kernel_ms;            /* device time of the solve kernel(s), CUDA events */
     float reset_ms;             /* device time of the total-cost reset */
 } dymu_solve_stats;
@@ -87,6 +89,10 @@ uint64_t dymu_launch_count(const dymu_ctx* ctx);
  * the elapsed milliseconds between two recorded events (synchronises on event b). */
 int dymu_event_record(dymu_ctx* ctx, int which);
 int dymu_event_elapsed_ms(dymu_ctx* ctx, int a, int b, float* ms);
+/* Self-test: compares the solver's branch-free square root with the IEEE sqrt on n
+ * pseudo-random positive normal doubles; *mismatches must come back 0. */
+int dymu_selftest_sqrt(dymu_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches,
+                       double* first_bad);
 /* Tile geometry of the solver: tile edge (cells), padded pitch (doubles per row). */
 int dymu_geometry(const dymu_ctx* ctx, uint32_t* tile, uint32_t* pitch, uint32_t* rows);
 

@@ -38,38 +38,24 @@ namespace
 {
 template <int TILE> struct Cfg
 {
-    static constexpr int THREADS = TILE * TILE / 4;
+    static_assert(TILE == 32, "16 warps x one 8x8 block each");
+    static constexpr int THREADS = 512;       // 16 warps
     static constexpr int WARPS = THREADS / 32;
-    static constexpr int BX = TILE / 8;   // warp blocks per tile row (8 cells wide)
-    static constexpr int BY = TILE / 4;   // warp blocks per tile column (4 cells tall)
-    static constexpr int NBLK = BX * BY;
-    static constexpr int BPW = NBLK / WARPS;  // = 4
-    // row pitch of the shared arrays in doubles; PITCH % 16 == 8 makes the four 8-double
-    // rows of a warp block fall into disjoint bank groups (conflict-free 64-bit access)
+    static constexpr int BX = TILE / 8;       // 4 x 4 blocks of 8 x 8 cells, block w <-> warp w
+    static constexpr int BY = TILE / 8;
+    // row pitch of the shared arrays in doubles; PITCH % 16 == 8 makes consecutive 8-double
+    // rows of a block fall into disjoint bank groups (conflict-free 64-bit access)
     static constexpr int PITCH = TILE + 8;
-    static constexpr int CPT = TILE * TILE / THREADS;  // cells per thread in load/store = 4
-    static constexpr int MIN_CTAS = (TILE == 32) ? 4 : 1;
-    static constexpr size_t SMEM = sizeof(double) * ((TILE + 2) * PITCH + TILE * PITCH) + 2 * NBLK;
+    static constexpr int CPT = TILE * TILE / THREADS;  // cells per thread in load/store = 2
+    static constexpr int MIN_CTAS = 2;
+    static constexpr size_t SMEM = sizeof(double) * ((TILE + 2) * PITCH + TILE * PITCH);
 };
-
-// warp block owned by (warp w, slot s): a bijection that spreads every row, column and
-// diagonal of blocks over distinct warps, so a straight wave front keeps all warps busy
-template <int TILE> __device__ __forceinline__ void block_of(int w, int s, int& bx, int& by);
-template <> __device__ __forceinline__ void block_of<32>(int w, int s, int& bx, int& by)
-{
-    bx = s;
-    by = (w - 2 * s) & 7;
-}
-template <> __device__ __forceinline__ void block_of<64>(int w, int s, int& bx, int& by)
-{
-    bx = 2 * s + (w & 1);
-    by = ((w >> 1) - 3 * bx) & 15;
-}
 
 constexpr uint32_t kLeftLanes = 0x01010101u, kRightLanes = 0x80808080u;
 constexpr uint32_t kTopLanes = 0x000000FFu, kBottomLanes = 0xFF000000u;
 // activation flag bits: which halo of the tile is stale / whole tile must be re-evaluated
-constexpr uint32_t kHaloTop = 1u, kHaloBottom = 2u, kHaloLeft = 4u, kHaloRight = 8u, kFull = 16u;
+constexpr uint32_t kHaloTop = 1u, kHaloBottom = 2u, kHaloLeft = 4u, kHaloRight = 8u, kFull = 16u,
+                   kResume = 32u;  // kResume: continue from the dirty mask saved in dsave[tile]
 
 struct Params
 {
@@ -83,14 +69,34 @@ struct Params
     uint32_t* flag0;
     uint32_t* flag1;
     uint32_t* flag2;
+    unsigned long long* key0;   // per tile: smallest value among the changes it was woken for
+    unsigned long long* key1;
+    unsigned long long* key2;
+    unsigned long long* gmin;   // [3] minimum key over each list
+    uint32_t* dsave;            // per tile: dirty-block mask left over when the sweep cap hit
+    unsigned long long* trace;  // optional: per phase {globaltimer ns, active tiles}, or nullptr
+    uint32_t trace_cap;
+    unsigned long long* cta_trace;  // optional (profile build): per phase x CTA timeline
+    uint32_t cta_trace_phases;
     uint32_t* ctrl;
     unsigned long long* stats;
     int inner_cap, max_outer;
+    double band;                // tiles with key > min key + band wait (inf = plain FIM)
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
 {
     return *reinterpret_cast<const volatile uint32_t*>(p);
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)
+{
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
+// non-negative doubles order like their bit patterns, so atomicMin on the bits is a min
+__device__ __forceinline__ unsigned long long key_of(double v)
+{
+    return (unsigned long long)__double_as_longlong(v);
 }
 
 // grid-wide barrier on a monotonically increasing arrival counter (all CTAs are
@@ -115,30 +121,62 @@ template <int MODE> __device__ __forceinline__ double outside_value()
     return MODE == 0 ? DYMU_INF : 0.0;  // missing neighbour: skipped (G.cpp:504-523) / risk 0 (L.cpp:555-558)
 }
 
-// one node update; returns true when the stored value improves
+// min / max of two non-negative doubles through their bit patterns (identical to fmin/fmax
+// for the values that occur here: finite >= 0 or +inf, never NaN) -- two integer
+// instructions instead of a DSETP + select chain on the critical path
+__device__ __forceinline__ double min_nn(double a, double b)
+{
+    long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+    return __longlong_as_double(x < y ? x : y);
+}
+__device__ __forceinline__ double max_nn(double a, double b)
+{
+    long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+    return __longlong_as_double(x > y ? x : y);
+}
+
+// One node update; returns true when the stored value improves.  Written branch-free so a
+// warp stays converged and two blocks can be interleaved: the two-sided (sqrt) value is
+// computed for every lane on a clamped argument and selected afterwards.  The value it
+// produces is bit-identical to propagateGlobalNode's (G.cpp:527-535):
+//   * `Tx < inf && Ty < inf` is implied by |Tx-Ty| < C for finite C (inf-inf is NaN);
+//   * C = +inf marks cells that are never targets (obstacles, padding): no update.
 template <int MODE>
 __device__ __forceinline__ bool relax(double tc, double tl, double tr, double tu, double td,
                                       double c, double& out)
 {
     if (MODE == 0)
     {
-        double Tx = fmin(tl, tr), Ty = fmin(td, tu);
-        double Tn = dymu_eikonal(Tx, Ty, c);
+        const double Tx = min_nn(tl, tr), Ty = min_nn(td, tu);
+        const double d = Tx - Ty;
+        const bool two = fabs(d) < c;             // false for NaN d (both inf) and for d = +-inf
+        const bool target = c < DYMU_INF;
+        double arg = (two && target) ? (2 * (c * c) - (d * d)) : 1.0;
+        // keep the select in front of the sqrt: hoisting it would feed -inf / NaN arguments
+        // into dsqrt and send the warp through the library's slow path at every wave front
+        asm volatile("" : "+d"(arg));
+        const double t2 = (Tx + Ty + dymu_sqrt_normal(arg)) / 2;  // arg in [c^2, 2c^2] or 1
+        const double t1 = min_nn(Tx, Ty) + c;
+        const double Tn = two ? t2 : t1;
         out = Tn;
-        return Tn < tc;
+        return target && (Tn < tc);
     }
     else
     {
         // propagateRisk, L.cpp:550-576; obstacle cells are never targets (c = +inf)
-        if (c == DYMU_INF) return false;
-        double Ry = fmax(tu, td), Rx = fmax(tl, tr);
-        double Sx = 1 - Rx, Sy = 1 - Ry, S;
-        double d = Sx - Sy;
-        if (fabs(d) < c) S = (Sx + Sy + sqrt(2 * (c * c) - (d * d))) / 2;
-        else S = fmin(Sx, Sy) + c;
-        double R = fmax(1 - S, 0.0);
+        const double Ry = max_nn(tu, td), Rx = max_nn(tl, tr);
+        const double Sx = 1 - Rx, Sy = 1 - Ry;
+        const double d = Sx - Sy;
+        const bool target = c < DYMU_INF;
+        const bool two = fabs(d) < c;
+        double arg = (two && target) ? (2 * (c * c) - (d * d)) : 1.0;
+        asm volatile("" : "+d"(arg));
+        const double s2 = (Sx + Sy + dymu_sqrt_normal(arg)) / 2;
+        const double s1 = fmin(Sx, Sy) + c;
+        const double S = two ? s2 : s1;
+        const double R = fmax(1 - S, 0.0);
         out = R;
-        return (R > 0) && (R > tc);
+        return target && (R > 0) && (R > tc);
     }
 }
 
@@ -150,15 +188,27 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ts = reinterpret_cast<double*>(smem_raw);            // (TILE+2) x P, 1-cell halo
     double* Cs = Ts + (TILE + 2) * P;                            // TILE x P
-    uint8_t(*dirty)[K::NBLK] = reinterpret_cast<uint8_t(*)[K::NBLK]>(Cs + TILE * P);
+    __shared__ uint32_t dmask[3];  // dirty 8x4 blocks: being swept / for the next sweep / being reset
     __shared__ uint32_t edge_changed[4];
-    __shared__ uint32_t s_idx;
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_emin[5];  // min changed value per edge [0..3], overall [4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_per_prob = p.ntx * p.nty;
     auto sel3 = [](uint32_t* a, uint32_t* b, uint32_t* c, int k) { return k == 0 ? a : (k == 1 ? b : c); };
+    auto sel3k = [](unsigned long long* a, unsigned long long* b, unsigned long long* c, int k) {
+        return k == 0 ? a : (k == 1 ? b : c);
+    };
     uint32_t phase = 0;
-    unsigned long long n_tiles = 0, n_visits = 0;
+    unsigned long long n_tiles = 0, n_visits = 0, n_deferred = 0, n_inner = 0;
+#ifdef DYMU_FIM_PROFILE
+    long long pc_fetch = 0, pc_load = 0, pc_sweep = 0, pc_store = 0, pc_barrier = 0, pc_t = clock64();
+#define PC_MARK(acc) { long long now__ = clock64(); acc += now__ - pc_t; pc_t = now__; }
+    unsigned long long tl_fetch = 0, tl_load = 0, tl_sweep = 0, tl_store = 0, tl_tiles = 0, tl_start = 0;
+#define GT(var) { unsigned long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); var = g__; }
+#else
+#define PC_MARK(acc)
+#endif
     int outer = 0;
     bool converged = false;
 
@@ -166,24 +216,74 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     {
         const int cur = outer % 3, nxt = (outer + 1) % 3, old = (outer + 2) % 3;
         const uint32_t n_active = ld_volatile_u32(&p.ctrl[cur]);
+        if (p.trace && blockIdx.x == 0 && tid == 0 && (uint32_t)outer < p.trace_cap)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[2 * outer] = t;
+            p.trace[2 * outer + 1] = n_active;
+        }
         if (n_active == 0)
         {
             converged = true;
             break;
         }
+#ifdef DYMU_FIM_PROFILE
+        if (tid == 0) { GT(tl_start) tl_fetch = tl_load = tl_sweep = tl_store = tl_start; tl_tiles = 0; }
+#endif
         uint32_t* list_cur = sel3(p.list0, p.list1, p.list2, cur);
         uint32_t* list_nxt = sel3(p.list0, p.list1, p.list2, nxt);
         uint32_t* flag_cur = sel3(p.flag0, p.flag1, p.flag2, cur);
         uint32_t* flag_nxt = sel3(p.flag0, p.flag1, p.flag2, nxt);
+        unsigned long long* key_cur = sel3k(p.key0, p.key1, p.key2, cur);
+        unsigned long long* key_nxt = sel3k(p.key0, p.key1, p.key2, nxt);
+        // priority band: only tiles whose pending information is within `band` of the
+        // smallest pending value anywhere are relaxed in this phase; the others are carried
+        // to the next list untouched.  This keeps tiles from being swept with halo values
+        // that are still far from final (the source of most re-activations in plain FIM).
+        unsigned long long limit = kNoKey;
+        {
+            const unsigned long long gm = ld_volatile_u64(&p.gmin[cur]);
+            const double lim = __longlong_as_double((long long)gm) + p.band;
+            if (gm != kNoKey && lim < DYMU_INF) limit = key_of(lim);
+        }
 
         for (;;)
         {
             __syncthreads();
-            if (tid == 0) s_idx = atomicAdd(&p.ctrl[3 + cur], 1u);
+            if (tid == 0)
+            {
+                uint32_t t = 0xffffffffu;
+                for (;;)
+                {
+                    const uint32_t idx = atomicAdd(&p.ctrl[3 + cur], 1u);
+                    if (idx >= n_active) break;
+                    const uint32_t cand = ld_volatile_u32(&list_cur[idx]);
+                    const unsigned long long k = ld_volatile_u64(&key_cur[cand]);
+                    if (k <= limit)
+                    {
+                        t = cand;
+                        break;
+                    }
+                    // defer: move flag bits and key to the next list
+                    const uint32_t bits = ld_volatile_u32(&flag_cur[cand]);
+                    flag_cur[cand] = 0;
+                    key_cur[cand] = kNoKey;
+                    atomicMin(&key_nxt[cand], k);
+                    atomicMin(&p.gmin[nxt], k);
+                    if (atomicOr(&flag_nxt[cand], bits) == 0)
+                        list_nxt[atomicAdd(&p.ctrl[nxt], 1u)] = cand;
+                    n_deferred++;
+                }
+                s_tile = t;
+            }
             __syncthreads();
-            const uint32_t idx = s_idx;
-            if (idx >= n_active) break;
-            const uint32_t tile_id = ld_volatile_u32(&list_cur[idx]);
+            PC_MARK(pc_fetch)
+            const uint32_t tile_id = s_tile;
+#ifdef DYMU_FIM_PROFILE
+            if (tid == 0 && tile_id != 0xffffffffu && tl_tiles == 0) GT(tl_fetch)
+#endif
+            if (tile_id == 0xffffffffu) break;
             const uint32_t prob = tile_id / tiles_per_prob;
             const uint32_t trem = tile_id - prob * tiles_per_prob;
             const uint32_t ty = trem / p.ntx, tx = trem - ty * p.ntx;
@@ -230,60 +330,78 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     Ts[(q + 1) * P + TILE + 1] = v;
                 }
             }
-            // initial dirty set: only the warp blocks along the stale halos, or everything
-            for (int b = tid; b < K::NBLK; b += K::THREADS)
+            // initial dirty set: the blocks along the stale halos (+ what an interrupted
+            // sweep left over), or everything for a seeded tile
+            if (tid == 0)
             {
-                int bx = b % K::BX, by = b / K::BX;
-                bool d = (why & kFull) || ((why & kHaloTop) && by == 0)
-                         || ((why & kHaloBottom) && by == K::BY - 1)
-                         || ((why & kHaloLeft) && bx == 0) || ((why & kHaloRight) && bx == K::BX - 1);
-                dirty[0][b] = d ? 1 : 0;
-                dirty[1][b] = 0;
+                uint32_t m0 = 0;
+                if (why & kResume) m0 |= p.dsave[tile_id];
+                if (why & kFull) m0 = 0xffffu;
+                if (why & kHaloTop) m0 |= 0x000Fu;                           // by == 0
+                if (why & kHaloBottom) m0 |= 0xF000u;                        // by == BY-1
+                if (why & kHaloLeft) m0 |= 0x1111u;                          // bx == 0
+                if (why & kHaloRight) m0 |= 0x8888u;                         // bx == BX-1
+                dmask[0] = m0;
+                dmask[1] = 0;
+                dmask[2] = 0;
+                flag_cur[tile_id] = 0;  // consumed; writers use flag_nxt / key_nxt this phase
+                key_cur[tile_id] = kNoKey;
             }
             if (tid < 4) edge_changed[tid] = 0;
-            if (tid == 0) flag_cur[tile_id] = 0;  // consumed; writers use flag_nxt this phase
+            if (tid < 5) s_emin[tid] = kNoKey;
             __syncthreads();
+            PC_MARK(pc_load)
+#ifdef DYMU_FIM_PROFILE
+            if (tid == 0 && tl_tiles == 0) GT(tl_load)
+#endif
 
-            // ---- relax in shared memory
-            int buf = 0, it = 0, more = 1;
-            while (more && it < p.inner_cap)
+            // ---- relax in shared memory.  Warp w owns the 8x8 block w (bx = w & 3, by = w >> 2);
+            // lane (lx, ly) owns the cells (lx, ly) and (lx, ly + 4) of it, whose two update
+            // chains are independent and interleave in the in-order issue stream.  A sweep is
+            // therefore one visit per warp, whatever the number of dirty blocks.
+            const int bx = warp & 3, by = warp >> 2;
+            const int lx = lane & 7, ly = lane >> 3;
+            const int oA = (by * 8 + ly + 1) * P + bx * 8 + lx + 1, oB = oA + 4 * P;
+            const double cA = Cs[(by * 8 + ly) * P + bx * 8 + lx], cB = Cs[(by * 8 + ly + 4) * P + bx * 8 + lx];
+            const uint32_t my_bit = 1u << warp;
+            int it = 0;
+            uint32_t m = dmask[0];
+            while (m != 0 && it < p.inner_cap)
             {
-                int any = 0;
-#pragma unroll
-                for (int s = 0; s < K::BPW; ++s)
+                const int nxt_m = (it + 1) % 3;
+                if (tid == 0) dmask[(it + 2) % 3] = 0;
+                if (m & my_bit)
                 {
-                    int bx, by;
-                    block_of<TILE>(warp, s, bx, by);
-                    const int b = by * K::BX + bx;
-                    if (!dirty[buf][b]) continue;  // warp-uniform
-                    __syncwarp();
-                    if (lane == 0) dirty[buf][b] = 0;
-                    const int x = bx * 8 + (lane & 7), y = by * 4 + (lane >> 3);
-                    const int o = (y + 1) * P + x + 1;
-                    double tn;
-                    bool ch = relax<MODE>(Ts[o], Ts[o - 1], Ts[o + 1], Ts[o - P], Ts[o + P],
-                                          Cs[y * P + x], tn);
-                    if (ch) Ts[o] = tn;
-                    const uint32_t m = __ballot_sync(0xffffffffu, ch);
-                    n_visits++;
-                    if (m)
+                    const double tA = Ts[oA], lA = Ts[oA - 1], rA = Ts[oA + 1], uA = Ts[oA - P], dA = Ts[oA + P];
+                    const double tB = Ts[oB], lB = Ts[oB - 1], rB = Ts[oB + 1], uB = Ts[oB - P], dB = Ts[oB + P];
+                    double nA, nB;
+                    const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA, nA);
+                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB, nB);
+                    if (chA) Ts[oA] = nA;
+                    if (chB) Ts[oB] = nB;
+                    const uint32_t mA = __ballot_sync(0xffffffffu, chA);
+                    const uint32_t mB = __ballot_sync(0xffffffffu, chB);
+                    n_visits += 2;
+                    if ((mA | mB) && lane == 0)
                     {
-                        any = 1;
-                        if (lane == 0)
-                        {
-                            uint8_t* dn = dirty[buf ^ 1];
-                            dn[b] = 1;
-                            if (m & kLeftLanes) { if (bx > 0) dn[b - 1] = 1; else edge_changed[2] = 1; }
-                            if (m & kRightLanes) { if (bx < K::BX - 1) dn[b + 1] = 1; else edge_changed[3] = 1; }
-                            if (m & kTopLanes) { if (by > 0) dn[b - K::BX] = 1; else edge_changed[0] = 1; }
-                            if (m & kBottomLanes) { if (by < K::BY - 1) dn[b + K::BX] = 1; else edge_changed[1] = 1; }
-                        }
+                        uint32_t bits = my_bit;
+                        if ((mA | mB) & kLeftLanes) { if (bx > 0) bits |= my_bit >> 1; else edge_changed[2] = 1; }
+                        if ((mA | mB) & kRightLanes) { if (bx < K::BX - 1) bits |= my_bit << 1; else edge_changed[3] = 1; }
+                        if (mA & kTopLanes) { if (by > 0) bits |= my_bit >> 4; else edge_changed[0] = 1; }
+                        if (mB & kBottomLanes) { if (by < K::BY - 1) bits |= my_bit << 4; else edge_changed[1] = 1; }
+                        atomicOr(&dmask[nxt_m], bits);
                     }
                 }
-                more = __syncthreads_or(any);
-                buf ^= 1;
+                __syncthreads();
                 ++it;
+                m = dmask[it % 3];
             }
+            const int more = (m != 0);
+            if (more && tid == 0) p.dsave[tile_id] = m;
+            PC_MARK(pc_sweep)
+#ifdef DYMU_FIM_PROFILE
+            if (tid == 0 && tl_tiles == 0) GT(tl_sweep)
+#endif
 
             // ---- write back changed cells and wake the neighbours whose halo went stale
 #pragma unroll
@@ -292,9 +410,23 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 int e = tid + k * K::THREADS;
                 int y = e / TILE, x = e % TILE;
                 double v = Ts[(y + 1) * P + x + 1];
-                if (v != told[k]) __stcg(&Tg[(size_t)y * p.pitch + x], v);
+                if (v != told[k])
+                {
+                    __stcg(&Tg[(size_t)y * p.pitch + x], v);
+                    if (MODE == 0)
+                    {
+                        // smallest new value per tile edge = the priority the neighbour gets
+                        const unsigned long long kb = key_of(v);
+                        if (y == 0) atomicMin(&s_emin[0], kb);
+                        if (y == TILE - 1) atomicMin(&s_emin[1], kb);
+                        if (x == 0) atomicMin(&s_emin[2], kb);
+                        if (x == TILE - 1) atomicMin(&s_emin[3], kb);
+                        if (more) atomicMin(&s_emin[4], kb);
+                    }
+                }
             }
             __threadfence();
+            __syncthreads();
             if (tid < 5)
             {
                 uint32_t target = 0xffffffffu, bit = 0;
@@ -302,9 +434,13 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 if (tid == 1 && edge_changed[1] && ty + 1 < p.nty) { target = tile_id + p.ntx; bit = kHaloTop; }
                 if (tid == 2 && edge_changed[2] && tx > 0) { target = tile_id - 1; bit = kHaloRight; }
                 if (tid == 3 && edge_changed[3] && tx + 1 < p.ntx) { target = tile_id + 1; bit = kHaloLeft; }
-                if (tid == 4 && more) { target = tile_id; bit = kFull; }  // cap hit: not converged
+                if (tid == 4 && more) { target = tile_id; bit = kResume; }  // cap hit: not converged
                 if (target != 0xffffffffu)
                 {
+                    unsigned long long kb = (MODE == 0) ? s_emin[tid] : 0ull;
+                    if (kb == kNoKey) kb = 0ull;  // (cannot happen: a flagged edge has a changed cell)
+                    atomicMin(&key_nxt[target], kb);
+                    atomicMin(&p.gmin[nxt], kb);
                     if (atomicOr(&flag_nxt[target], bit) == 0)
                     {
                         uint32_t pos = atomicAdd(&p.ctrl[nxt], 1u);
@@ -313,20 +449,49 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 }
             }
             n_tiles++;
+            n_inner += (unsigned long long)it;
+            PC_MARK(pc_store)
+#ifdef DYMU_FIM_PROFILE
+            if (tid == 0) { GT(tl_store) tl_tiles++; }
+#endif
         }
+        PC_MARK(pc_fetch)
+#ifdef DYMU_FIM_PROFILE
+        if (tid == 0 && p.cta_trace && (uint32_t)outer < p.cta_trace_phases)
+        {
+            unsigned long long tl_arrive; GT(tl_arrive)
+            unsigned long long* o = p.cta_trace + ((size_t)outer * gridDim.x + blockIdx.x) * 8;
+            o[0] = tl_start; o[1] = tl_fetch; o[2] = tl_load; o[3] = tl_sweep; o[4] = tl_store;
+            o[5] = tl_arrive; o[6] = tl_tiles; o[7] = n_active;
+        }
+#endif
         if (blockIdx.x == 0 && tid == 0)
         {
             p.ctrl[old] = 0;      // count of the list that becomes "next" after this barrier
             p.ctrl[3 + old] = 0;  // and its cursor
+            p.gmin[old] = kNoKey;
         }
         grid_barrier(&p.ctrl[6], phase);
+        PC_MARK(pc_barrier)
     }
+#ifdef DYMU_FIM_PROFILE
+    if (tid == 0)
+    {
+        atomicAdd(&p.stats[8], (unsigned long long)pc_fetch);
+        atomicAdd(&p.stats[9], (unsigned long long)pc_load);
+        atomicAdd(&p.stats[10], (unsigned long long)pc_sweep);
+        atomicAdd(&p.stats[11], (unsigned long long)pc_store);
+        atomicAdd(&p.stats[12], (unsigned long long)pc_barrier);
+    }
+#endif
 
     // ---- statistics
     if (lane == 0 && n_visits) atomicAdd(&p.stats[1], n_visits);
     if (tid == 0)
     {
         if (n_tiles) atomicAdd(&p.stats[0], n_tiles);
+        if (n_deferred) atomicAdd(&p.stats[4], n_deferred);
+        if (n_inner) atomicAdd(&p.stats[5], n_inner);
         if (blockIdx.x == 0)
         {
             p.stats[2] = (unsigned long long)outer;
@@ -337,7 +502,8 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 
 __global__ void k_seed(double* T, size_t slot_stride, uint32_t pitch, uint32_t ntx, uint32_t nty,
                        int tile, const uint32_t* goal_ij, uint32_t n, uint32_t* list0,
-                       uint32_t* flag0, uint32_t* ctrl)
+                       uint32_t* flag0, unsigned long long* key0, unsigned long long* gmin,
+                       uint32_t* ctrl)
 {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -345,20 +511,31 @@ __global__ void k_seed(double* T, size_t slot_stride, uint32_t pitch, uint32_t n
     T[(size_t)q * slot_stride + (size_t)gj * pitch + gi] = 0.0;  // resetGlobalNarrowBand, G.cpp:490-496
     uint32_t tile_id = q * ntx * nty + (gj / tile) * ntx + gi / tile;
     flag0[tile_id] = kFull;
+    key0[tile_id] = 0ull;
     list0[q] = tile_id;
-    if (q == 0) ctrl[0] = n;
+    if (q == 0)
+    {
+        ctrl[0] = n;
+        gmin[0] = 0ull;
+    }
 }
 
 __global__ void k_seed_rows(uint32_t ntx, uint32_t ty0, uint32_t ty1, uint32_t* list0,
-                            uint32_t* flag0, uint32_t* ctrl)
+                            uint32_t* flag0, unsigned long long* key0, unsigned long long* gmin,
+                            uint32_t* ctrl)
 {
     uint32_t n = (ty1 - ty0) * ntx;
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     uint32_t tile_id = ty0 * ntx + q;
     flag0[tile_id] = kFull;
+    key0[tile_id] = 0ull;
     list0[q] = tile_id;
-    if (q == 0) ctrl[0] = n;
+    if (q == 0)
+    {
+        ctrl[0] = n;
+        gmin[0] = 0ull;
+    }
 }
 
 template <int TILE, int MODE> int launch_fim(dymu_ctx* ctx, Params& prm, size_t total_tiles)
@@ -393,9 +570,15 @@ int dymu_internal_fim_alloc(dymu_ctx* ctx, dymu_fim_work* w, size_t capacity)
         DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->list[k], capacity * sizeof(uint32_t)));
         DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->flag[k], capacity * sizeof(uint32_t)));
         DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->flag[k], 0, capacity * sizeof(uint32_t), ctx->stream));
+        DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->key[k], capacity * sizeof(unsigned long long)));
+        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->key[k], 0xFF, capacity * sizeof(unsigned long long),
+                                           ctx->stream));
     }
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->ctrl, 8 * sizeof(uint32_t)));
-    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->stats, 4 * sizeof(unsigned long long)));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->gmin, 4 * sizeof(unsigned long long)));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->dsave, capacity * sizeof(uint32_t)));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->dsave, 0, capacity * sizeof(uint32_t), ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->stats, 16 * sizeof(unsigned long long)));
     return DYMU_OK;
 }
 
@@ -405,9 +588,15 @@ void dymu_internal_fim_free(dymu_fim_work* w)
     {
         if (w->list[k]) cudaFree(w->list[k]);
         if (w->flag[k]) cudaFree(w->flag[k]);
+        if (w->key[k]) cudaFree(w->key[k]);
         w->list[k] = w->flag[k] = nullptr;
+        w->key[k] = nullptr;
     }
     if (w->ctrl) cudaFree(w->ctrl);
+    if (w->gmin) cudaFree(w->gmin);
+    if (w->dsave) cudaFree(w->dsave);
+    w->gmin = nullptr;
+    w->dsave = nullptr;
     if (w->stats) cudaFree(w->stats);
     w->ctrl = nullptr;
     w->stats = nullptr;
@@ -426,6 +615,9 @@ int dymu_internal_fim_configure(dymu_ctx* ctx)
     if (const char* e = getenv("DYMU_FIM_GRID_PER_SM"))
         if (atoi(e) > 0) ctx->fim_grid_per_sm = atoi(e);
     ctx->fim_max_outer = 0;  // derived per launch
+    ctx->fim_band_factor = 4.0;  // band = factor * tile * mean(C_eff); <= 0 disables banding
+    if (const char* e = getenv("DYMU_FIM_BAND")) ctx->fim_band_factor = atof(e);
+    ctx->fim_band = 1.0 / 0.0;
     return DYMU_OK;
 }
 
@@ -444,8 +636,39 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     prm.nprob = L.nprob;
     prm.list0 = w->list[0]; prm.list1 = w->list[1]; prm.list2 = w->list[2];
     prm.flag0 = w->flag[0]; prm.flag1 = w->flag[1]; prm.flag2 = w->flag[2];
+    prm.key0 = w->key[0]; prm.key1 = w->key[1]; prm.key2 = w->key[2];
+    prm.gmin = w->gmin;
+    prm.dsave = w->dsave;
+    prm.trace = nullptr;
+    prm.trace_cap = 0;
+    prm.cta_trace = nullptr;
+    prm.cta_trace_phases = 0;
+    unsigned long long* d_cta_trace = nullptr;
+    const uint32_t cta_trace_phases = 400;
+    const char* cta_trace_path = getenv("DYMU_FIM_CTA_TRACE");
+#ifdef DYMU_FIM_PROFILE
+    if (cta_trace_path && L.mode == 0)
+    {
+        size_t bytes = (size_t)cta_trace_phases * 1024 * 8 * 8;
+        DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&d_cta_trace, bytes));
+        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d_cta_trace, 0, bytes, ctx->stream));
+        prm.cta_trace = d_cta_trace;
+        prm.cta_trace_phases = cta_trace_phases;
+    }
+#endif
+    const char* trace_path = getenv("DYMU_FIM_TRACE");
+    unsigned long long* d_trace = nullptr;
+    const uint32_t trace_cap = 8192;
+    if (trace_path && L.mode == 0)
+    {
+        DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&d_trace, trace_cap * 16));
+        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d_trace, 0, trace_cap * 16, ctx->stream));
+        prm.trace = d_trace;
+        prm.trace_cap = trace_cap;
+    }
     prm.ctrl = w->ctrl;
     prm.stats = w->stats;
+    prm.band = L.band;
     prm.inner_cap = ctx->fim_inner_cap;
     // a wave needs at most ~(ntx+nty) tile hops in free space; obstacles lengthen the
     // geodesic, so leave two orders of magnitude of head room before reporting NOCONV
@@ -455,19 +678,58 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     size_t total_tiles = (size_t)L.ntx * L.nty * L.nprob;
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     int rc;
-    if (L.tile == 32) rc = (L.mode == 0) ? launch_fim<32, 0>(ctx, prm, total_tiles) : launch_fim<32, 1>(ctx, prm, total_tiles);
-    else rc = (L.mode == 0) ? launch_fim<64, 0>(ctx, prm, total_tiles) : launch_fim<64, 1>(ctx, prm, total_tiles);
+    if (L.tile != 32) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unsupported tile edge %d", L.tile);
+    rc = (L.mode == 0) ? launch_fim<32, 0>(ctx, prm, total_tiles) : launch_fim<32, 1>(ctx, prm, total_tiles);
     DYMU_TRY(rc);
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
-    unsigned long long h[4];
+    unsigned long long h[16];
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, w->stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+#ifdef DYMU_FIM_PROFILE
+    if (L.mode == 0)
+    {
+        double tot = (double)(h[8] + h[9] + h[10] + h[11] + h[12]);
+        fprintf(stderr, "[fim profile] cycles/CTA-sum: fetch %.1f%% load %.1f%% sweep %.1f%% store %.1f%% barrier %.1f%%;"
+                " per activation: load %.0f sweep %.0f store %.0f cyc; per sweep %.0f cyc; fetch+barrier per CTA-phase %.0f cyc\n",
+                100 * h[8] / tot, 100 * h[9] / tot, 100 * h[10] / tot, 100 * h[11] / tot, 100 * h[12] / tot,
+                (double)h[9] / h[0], (double)h[10] / h[0], (double)h[11] / h[0], (double)h[10] / (h[5] ? h[5] : 1),
+                (double)(h[8] + h[12]) / ((double)h[2] * 444));
+    }
+#endif
+    if (d_cta_trace)
+    {
+        size_t bytes = (size_t)cta_trace_phases * 1024 * 8 * 8;
+        void* hb = malloc(bytes);
+        cudaMemcpy(hb, d_cta_trace, bytes, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(cta_trace_path, "wb"))
+        {
+            fwrite(hb, 1, bytes, f);
+            fclose(f);
+        }
+        free(hb);
+        cudaFree(d_cta_trace);
+    }
+    if (d_trace)
+    {
+        unsigned long long* ht = (unsigned long long*)malloc(trace_cap * 16);
+        cudaMemcpy(ht, d_trace, trace_cap * 16, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(trace_path, "w"))
+        {
+            for (uint32_t k = 0; k < trace_cap && ht[2 * k]; ++k)
+                fprintf(f, "%u %llu %llu\n", k, ht[2 * k] - ht[0], ht[2 * k + 1]);
+            fclose(f);
+        }
+        free(ht);
+        cudaFree(d_trace);
+    }
     if (stats)
     {
         stats->tile_activations = h[0];
-        stats->cell_updates = h[1] * 32ull;
+        stats->cell_updates = h[1] * 32ull;  // n_visits counts 32-cell warp evaluations
         stats->outer_iterations = (uint32_t)h[2];
         stats->converged = (uint32_t)h[3];
+        stats->tiles_deferred = h[4];
+        stats->inner_iterations = h[5];
         DYMU_CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev1, ctx->ev2));
     }
     if (!h[3])
@@ -478,14 +740,57 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
 
 int dymu_internal_fill(dymu_ctx* ctx, double* p, double v, size_t n);
 
-static int reset_work(dymu_ctx* ctx, dymu_fim_work* w)
+int dymu_internal_fim_reset(dymu_ctx* ctx, dymu_fim_work* w)
 {
     DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->ctrl, 0, 8 * sizeof(uint32_t), ctx->stream));
-    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->gmin, 0xFF, 4 * sizeof(unsigned long long), ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->stats, 0, 16 * sizeof(unsigned long long), ctx->stream));
     return DYMU_OK;
 }
+static int reset_work(dymu_ctx* ctx, dymu_fim_work* w) { return dymu_internal_fim_reset(ctx, w); }
+
+namespace
+{
+__global__ void k_selftest_sqrt(unsigned long long seed, unsigned long long n, unsigned long long* bad,
+                                double* first_bad)
+{
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+    {
+        // splitmix64 -> mantissa + an exponent spread over 2^-120 .. 2^120
+        unsigned long long z = seed + (k + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        unsigned long long mant = z & 0x000FFFFFFFFFFFFFull;
+        unsigned long long ex = 1023ull - 120ull + ((z >> 52) % 241ull);
+        double x = __longlong_as_double((long long)((ex << 52) | mant));
+        if ((k & 7) == 0) x = (double)((z >> 40) & 0xFFFFFF) * (double)((z >> 40) & 0xFFFFFF) + 0.0;  // perfect squares
+        if (x <= 0) x = 1.0;
+        double a = dymu_sqrt_normal(x), b = sqrt(x);
+        if (__double_as_longlong(a) != __double_as_longlong(b))
+            if (atomicAdd(bad, 1ull) == 0) *first_bad = x;
+    }
+}
+}  // namespace
 
 extern "C" {
+
+int dymu_selftest_sqrt(dymu_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches, double* first_bad)
+{
+    if (!ctx || !mismatches) return DYMU_ERR_ARG;
+    unsigned long long* d = (unsigned long long*)ctx->d_scratch;
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    k_selftest_sqrt<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(seed, n, d, (double*)(d + 1));
+    ctx->launches++;
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    unsigned long long h[2];
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = h[0];
+    if (first_bad) memcpy(first_bad, &h[1], 8);
+    return DYMU_OK;
+}
 
 int dymu_reserve_slots(dymu_ctx* ctx, uint32_t n_slots)
 {
@@ -528,13 +833,14 @@ int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_
                                        cudaMemcpyHostToDevice, ctx->stream));
     k_seed<<<dymu_div_up(n_goals, 128), 128, 0, ctx->stream>>>(
         ctx->T, n, ctx->pitch, ctx->ntx, ctx->nty, (int)ctx->tile, (const uint32_t*)ctx->d_scratch,
-        n_goals, ctx->work.list[0], ctx->work.flag[0], ctx->work.ctrl);
+        n_goals, ctx->work.list[0], ctx->work.flag[0], ctx->work.key[0], ctx->work.gmin,
+        ctx->work.ctrl);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     dymu_fim_launch L;
     L.T = ctx->T; L.slot_stride = n; L.C = ctx->ceff; L.pitch = ctx->pitch; L.rows = ctx->rows;
     L.ntx = ctx->ntx; L.nty = ctx->nty; L.nprob = n_goals; L.mode = 0; L.tile = (int)ctx->tile;
-    L.work = &ctx->work; L.n_initial = n_goals;
+    L.work = &ctx->work; L.n_initial = n_goals; L.band = ctx->fim_band;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     int rc = dymu_internal_fim_run(ctx, L, &local);
@@ -556,13 +862,14 @@ int dymu_solve_resume(dymu_ctx* ctx, uint32_t j0, uint32_t j1, dymu_solve_stats*
     uint32_t ty0 = j0 / ctx->tile, ty1 = dymu_div_up(j1, ctx->tile);
     uint32_t ntl = (ty1 - ty0) * ctx->ntx;
     k_seed_rows<<<dymu_div_up(ntl, 128), 128, 0, ctx->stream>>>(ctx->ntx, ty0, ty1, ctx->work.list[0],
-                                                                ctx->work.flag[0], ctx->work.ctrl);
+                                                                ctx->work.flag[0], ctx->work.key[0],
+                                                                ctx->work.gmin, ctx->work.ctrl);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     dymu_fim_launch L;
     L.T = ctx->T; L.slot_stride = (size_t)ctx->pitch * ctx->rows; L.C = ctx->ceff;
     L.pitch = ctx->pitch; L.rows = ctx->rows; L.ntx = ctx->ntx; L.nty = ctx->nty; L.nprob = 1;
-    L.mode = 0; L.tile = (int)ctx->tile; L.work = &ctx->work; L.n_initial = ntl;
+    L.mode = 0; L.tile = (int)ctx->tile; L.work = &ctx->work; L.n_initial = ntl; L.band = ctx->fim_band;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     int rc = dymu_internal_fim_run(ctx, L, &local);

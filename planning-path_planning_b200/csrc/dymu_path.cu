@@ -3,15 +3,27 @@
 // interpolate, src/DyMu_GlobalPathPlanning.cpp:615-784).
 //
 // The descent is a sequential chain (each waypoint depends on the previous one), so it is
-// latency-bound, not bandwidth-bound: one warp walks one path.  Lanes 0..3 evaluate the
-// four cell-corner gradients in parallel (each gathers its own 5-point stencil of T),
-// the results are exchanged with warp shuffles and every lane carries the identical
-// waypoint state, so there is no divergence; lane 0 stores the waypoint.  Batches of
-// queries run one warp per query.
+// latency-bound, not bandwidth-bound: one warp walks one path.  The warp keeps a
+// PATCH x PATCH window of T and of the elevation in shared memory and re-centres it only
+// when the 4x4 stencil of the current cell leaves it (a 0.4-cell step stays inside for
+// ~100 steps), so the per-step loads are shared-memory hits.  Lanes 0..3 evaluate the four
+// cell-corner gradients in parallel, the results are exchanged with warp shuffles and every
+// lane carries the identical waypoint state, so there is no divergence; lane 0 stores the
+// waypoint.  Batches of queries run one warp (one CTA) per query.
 #include "dymu_ctx.cuh"
 
 namespace
 {
+constexpr int PATCH = 64;  // cells per patch edge: 2 x 32 KB of shared memory
+
+struct Patch
+{
+    double* t;   // PATCH x PATCH total cost
+    double* e;   // PATCH x PATCH elevation
+    int x0, y0;  // grid coordinates of patch cell (0,0); valid region clipped to the grid
+    bool valid;
+};
+
 struct PathArgs
 {
     const double* T;
@@ -41,14 +53,14 @@ __device__ __forceinline__ double grad_axis(double f, bool has_lo, double flo, b
 }
 
 // gradientNode(globalNode*), G.cpp:718-772
-__device__ __forceinline__ void grad_node(const PathArgs& a, uint32_t i, uint32_t j, double& dnx,
-                                          double& dny)
+__device__ __forceinline__ void grad_node(const PathArgs& a, const Patch& pt, uint32_t i, uint32_t j,
+                                          double& dnx, double& dny)
 {
-    const double* Tc = a.T + (size_t)j * a.pitch + i;
-    double f = __ldcg(Tc);
+    const double* Tc = pt.t + ((int)j - pt.y0) * PATCH + ((int)i - pt.x0);
+    double f = *Tc;
     bool hl = i > 0, hr = i + 1 < a.nx, hd = j > 0, hu = j + 1 < a.ny;
-    double fl = hl ? __ldcg(Tc - 1) : 0, fr = hr ? __ldcg(Tc + 1) : 0;
-    double fd = hd ? __ldcg(Tc - a.pitch) : 0, fu = hu ? __ldcg(Tc + a.pitch) : 0;
+    double fl = hl ? Tc[-1] : 0, fr = hr ? Tc[1] : 0;
+    double fd = hd ? Tc[-PATCH] : 0, fu = hu ? Tc[PATCH] : 0;
     double dx = grad_axis(f, hl, fl, hr, fr);
     double dy = grad_axis(f, hd, fd, hu, fu);
     if ((dx == 0) && (dy == 0))
@@ -65,21 +77,50 @@ __device__ __forceinline__ void grad_node(const PathArgs& a, uint32_t i, uint32_
 }
 
 // computeNextGlobalWaypoint, G.cpp:666-714.  Returns false if the cell leaves the grid.
-__device__ __forceinline__ bool next_waypoint(const PathArgs& a, int lane, double wx, double wy,
-                                              double& z, double& dCx, double& dCy, double& nx_,
-                                              double& ny_)
+// (re)loads the shared-memory window so that cells [cx-1, cx+2] x [cy-1, cy+2] are inside
+__device__ __forceinline__ void ensure_patch(const PathArgs& a, Patch& pt, int lane, int cx, int cy)
+{
+    if (pt.valid && cx - 1 >= pt.x0 && cy - 1 >= pt.y0 && cx + 2 < pt.x0 + PATCH && cy + 2 < pt.y0 + PATCH)
+        return;
+    __syncwarp();
+    pt.x0 = cx - PATCH / 2;
+    pt.y0 = cy - PATCH / 2;
+    pt.valid = true;
+    for (int r = 0; r < PATCH; ++r)
+    {
+        int gy = pt.y0 + r;
+        for (int c = lane; c < PATCH; c += 32)
+        {
+            int gx = pt.x0 + c;
+            double tv = DYMU_INF, ev = 0.0;
+            if (gx >= 0 && gy >= 0 && gx < (int)a.nx && gy < (int)a.ny)
+            {
+                tv = __ldcg(a.T + (size_t)gy * a.pitch + gx);
+                ev = a.elev[(size_t)gy * a.pitch + gx];
+            }
+            pt.t[r * PATCH + c] = tv;
+            pt.e[r * PATCH + c] = ev;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ bool next_waypoint(const PathArgs& a, Patch& pt, int lane, double wx,
+                                              double wy, double& z, double& dCx, double& dCy,
+                                              double& nx_, double& ny_)
 {
     double gx = wx / a.gres, gy = wy / a.gres;
     if (!(gx >= 0.0) || !(gy >= 0.0) || !(gx < (double)(a.nx - 1)) || !(gy < (double)(a.ny - 1)))
         return false;
     uint32_t cx = (uint32_t)gx, cy = (uint32_t)gy;
     double da = gx - (double)cx, db = gy - (double)cy;
+    ensure_patch(a, pt, lane, (int)cx, (int)cy);
     // lane c (0..3) owns corner (cx + (c&1), cy + (c>>1)): 0=n00 1=n10 2=n01 3=n11
     int c = lane & 3;
     uint32_t ci = cx + (uint32_t)(c & 1), cj = cy + (uint32_t)(c >> 1);
     double gxc, gyc;
-    grad_node(a, ci, cj, gxc, gyc);
-    double ec = a.elev[(size_t)cj * a.pitch + ci];
+    grad_node(a, pt, ci, cj, gxc, gyc);
+    double ec = pt.e[((int)cj - pt.y0) * PATCH + ((int)ci - pt.x0)];
     const unsigned full = 0xffffffffu;
     double gx00 = __shfl_sync(full, gxc, 0), gx10 = __shfl_sync(full, gxc, 1);
     double gx01 = __shfl_sync(full, gxc, 2), gx11 = __shfl_sync(full, gxc, 3);
@@ -107,6 +148,12 @@ __global__ void __launch_bounds__(32, 1) k_global_path(const PathArgs* args_arr)
 {
     const PathArgs a = args_arr[blockIdx.x];
     const int lane = threadIdx.x;
+    extern __shared__ __align__(16) double path_smem[];
+    Patch pt;
+    pt.t = path_smem;
+    pt.e = path_smem + PATCH * PATCH;
+    pt.x0 = pt.y0 = 0;
+    pt.valid = false;
     const double sx = a.gres * (double)a.goal_i, sy = a.gres * (double)a.goal_j;
     uint32_t n = 0, status = DYMU_PATH_OK;
     double wx = a.x0, wy = a.y0, z, dCx, dCy, nx_, ny_;
@@ -122,7 +169,7 @@ __global__ void __launch_bounds__(32, 1) k_global_path(const PathArgs* args_arr)
         return true;
     };
 
-    if (!next_waypoint(a, lane, wx, wy, z, dCx, dCy, nx_, ny_)) status = DYMU_PATH_OUTSIDE;
+    if (!next_waypoint(a, pt, lane, wx, wy, z, dCx, dCy, nx_, ny_)) status = DYMU_PATH_OUTSIDE;
     else if (isnan(nx_) || isnan(ny_)) status = DYMU_PATH_NAN;
     else
     {
@@ -131,7 +178,7 @@ __global__ void __launch_bounds__(32, 1) k_global_path(const PathArgs* args_arr)
         wy = ny_;
         while (dist2d(wx, wy, sx, sy) > 2.0 * a.gres)
         {
-            if (!next_waypoint(a, lane, wx, wy, z, dCx, dCy, nx_, ny_))
+            if (!next_waypoint(a, pt, lane, wx, wy, z, dCx, dCy, nx_, ny_))
             {
                 status = DYMU_PATH_OUTSIDE;
                 break;
@@ -185,7 +232,10 @@ int dymu_extract_global_path(dymu_ctx* ctx, uint32_t slot, double x0, double y0,
     *h_args = a;
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, h_args, sizeof(PathArgs),
                                        cudaMemcpyHostToDevice, ctx->stream));
-    k_global_path<<<1, 32, 0, ctx->stream>>>((const PathArgs*)ctx->d_scratch);
+    const size_t smem = 2 * PATCH * PATCH * sizeof(double);
+    DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(k_global_path, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+    k_global_path<<<1, 32, smem, ctx->stream>>>((const PathArgs*)ctx->d_scratch);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     uint32_t* h_res = (uint32_t*)((char*)ctx->h_pinned + sizeof(PathArgs));

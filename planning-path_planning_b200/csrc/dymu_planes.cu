@@ -195,6 +195,32 @@ __global__ void k_ceff(const double* __restrict__ cost, const double* __restrict
     }
 }
 
+// sum and count of the finite C_eff values (sets the width of the solver's priority band)
+__global__ void k_ceff_stats(const double* __restrict__ ceff, size_t n, double* out)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    double sum = 0, cnt = 0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    {
+        double c = ceff[q];
+        if (c < DYMU_INF)
+        {
+            sum += c;
+            cnt += 1.0;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0)
+    {
+        atomicAdd(&out[0], sum);
+        atomicAdd(&out[1], cnt);
+    }
+}
+
 // dense read-back with the getter transforms of G.cpp:799-829.  8(+17) B read, 8 B written.
 __global__ void k_readback(const double* __restrict__ src, const double* __restrict__ haz,
                            const double* __restrict__ traff, const uint8_t* __restrict__ obst,
@@ -347,8 +373,6 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
     ctx->gres = global_res;
     ctx->lres = local_res;
     ctx->tile = 32;
-    if (const char* t = getenv("DYMU_FIM_TILE"))
-        if (atoi(t) == 64) ctx->tile = 64;
     ctx->ntx = dymu_div_up(nx, ctx->tile);
     ctx->nty = dymu_div_up(ny, ctx->tile);
     ctx->pitch = ctx->ntx * ctx->tile;
@@ -739,6 +763,20 @@ int dymu_internal_refresh_ceff(dymu_ctx* ctx)
                                                              ctx->ny);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    // band width of the tile scheduler: a few tile crossings worth of total cost
+    ctx->fim_band = 1.0 / 0.0;
+    if (ctx->fim_band_factor > 0)
+    {
+        double* d = (double*)ctx->d_scratch;
+        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+        k_ceff_stats<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->ceff, n, d);
+        ctx->launches++;
+        DYMU_CUDA_TRY(ctx, cudaGetLastError());
+        double h[2] = {0, 0};
+        DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h[1] > 0) ctx->fim_band = ctx->fim_band_factor * (double)ctx->tile * (h[0] / h[1]);
+    }
     ctx->ceff_dirty = false;
     return DYMU_OK;
 }

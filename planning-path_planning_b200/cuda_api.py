@@ -27,7 +27,7 @@ _u32p = C.POINTER(C.c_uint32)
 class SolveStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_uint32), ("converged", C.c_uint32),
                 ("tile_activations", C.c_uint64), ("cell_updates", C.c_uint64),
-                ("cells_reached", C.c_uint64), ("kernel_ms", C.c_float), ("reset_ms", C.c_float)]
+                ("cells_reached", C.c_uint64), ("tiles_deferred", C.c_uint64), ("inner_iterations", C.c_uint64), ("kernel_ms", C.c_float), ("reset_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -43,6 +43,7 @@ _SIG = {
     "dymu_launch_count": (C.c_uint64, [C.c_void_p]),
     "dymu_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "dymu_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "dymu_selftest_sqrt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), _dp]),
     "dymu_geometry": (C.c_int, [C.c_void_p, _u32p, _u32p, _u32p]),
     "dymu_upload_plane": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t]),
     "dymu_download_plane": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t, C.c_int]),
@@ -176,6 +177,11 @@ class DeviceLayer:
         ms = C.c_float()
         self._chk(self._l.dymu_event_elapsed_ms(self._h, a, b, C.byref(ms)))
         return ms.value
+
+    def selftest_sqrt(self, n, seed=1):
+        bad, first = C.c_uint64(), C.c_double()
+        self._chk(self._l.dymu_selftest_sqrt(self._h, n, seed, C.byref(bad), C.byref(first)))
+        return int(bad.value), first.value
 
     def geometry(self):
         t, p, r = C.c_uint32(), C.c_uint32(), C.c_uint32()

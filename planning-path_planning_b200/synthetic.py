@@ -41,7 +41,7 @@ def _add_craters(elev, n_craters, rng, rmin=4.0, rmax=40.0):
             continue
         yy, xx = np.mgrid[y0:y1, x0:x1]
         d = np.sqrt((xx - cx) ** 2 + (yy - cy) ** 2) / r
-        depth = 0.2 * r
+        depth = rng.uniform(0.13, 0.2) * r
         bowl = np.where(d < 1.0, -depth * (1.0 - d * d), 0.0)
         rim = 0.25 * depth * np.exp(-((d - 1.0) / 0.18) ** 2)
         elev[y0:y1, x0:x1] += bowl + rim
@@ -68,7 +68,9 @@ def mars_dem(ny, nx, seed=DEFAULT_SEED, rms_slope_deg=8.0, craters=None):
     rms = np.sqrt(np.mean(gx * gx + gy * gy))
     elev *= np.tan(np.deg2rad(rms_slope_deg)) / rms
     if craters is None:
-        craters = max(1, max(nx, ny) // 64)
+        # constant areal density (a count that grows only with the edge length would let the
+        # obstacle fraction fall with the map size)
+        craters = max(1, int(round(0.85 * nx * ny / 4096.0)))
     _add_craters(elev, craters, rng)
     tfield = fbm(ny, nx, 3.0, rng)
     q = np.quantile(tfield, [0.4, 0.7, 0.9])

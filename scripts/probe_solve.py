@@ -15,6 +15,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--kind", default="mars")
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--nopath", action="store_true")
 args = ap.parse_args()
 
 pkg = dymu_b200.load()
@@ -46,10 +47,13 @@ if args.batch > 1:
 for r in range(args.reps):
     st = dev.solve_total_cost(goals)
     reached = dev.count_reached()
-    print("rep %d: kernel %.3f ms reset %.3f ms outer %d tiles %d updates %.3e (%.1f/cell) reached %.4f conv %d"
+    print("rep %d: kernel %.3f ms reset %.3f ms outer %d tiles %d deferred %d inner/tile %.1f updates %.3e (%.1f/cell) reached %.4f conv %d"
           % (r, st["kernel_ms"], st["reset_ms"], st["outer_iterations"], st["tile_activations"],
+             st["tiles_deferred"], st["inner_iterations"] / max(1, st["tile_activations"]),
              st["cell_updates"], st["cell_updates"] / (n * n * len(goals)), reached / (n * n),
              st["converged"]), flush=True)
+if args.nopath:
+    sys.exit(0)
 si, sj = syn.free_interior_cell_near(ob, n // 8, n // 8)
 t = time.time()
 wps, status = dev.extract_global_path(float(si), float(sj), 0.4, goals[0][0], goals[0][1])
