@@ -135,8 +135,20 @@ int dymu_reserve_slots(dymu_ctx* ctx, uint32_t n_slots);
 int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_i,
                           const uint32_t* goal_j, dymu_solve_stats* stats);
 /* Continue a solve after total-cost values were lowered from outside (domain
- * decomposition halo rows): re-activates the tiles covering rows [j0, j1) of slot 0. */
-int dymu_solve_resume(dymu_ctx* ctx, uint32_t j0, uint32_t j1, dymu_solve_stats* stats);
+ * decomposition halo rows): re-activates the tiles covering the row ranges
+ * [ranges[2k], ranges[2k+1]) of slot 0 and iterates to convergence. */
+int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges,
+                      dymu_solve_stats* stats);
+/* resetTotalCostMap (G.cpp:473-485) without seeding a goal: every slot-0 value = +inf. */
+int dymu_reset_total_cost(dymu_ctx* ctx);
+/* Halo exchange for row-strip domain decomposition.  Rows are dense (nx doubles each).
+ * `device_ptr` != 0: dst/src is device memory of this GPU, otherwise host memory.
+ * import takes the element-wise minimum with the resident rows and reports whether any
+ * value decreased. */
+int dymu_export_rows(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows, double* dst,
+                     int device_ptr);
+int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
+                         const double* src, int device_ptr, int* changed);
 int dymu_count_reached(dymu_ctx* ctx, uint32_t slot, uint64_t* n_finite);
 /* CLOSED-set emulation of the early stop in computeTotalCostMap (G.cpp:390): returns
  * T_stop = max over the start node and its 4 neighbours; cells with T <= T_stop are the

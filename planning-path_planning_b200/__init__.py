@@ -16,7 +16,7 @@ repository root (module name ``planning_path_planning_b200``).
 import os
 
 from . import build as build_tools
-from . import cuda_api, planner_api, synthetic
+from . import cuda_api, planner_api, sharding, synthetic
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_SO = os.path.join(HERE, "libdymu_b200.so")

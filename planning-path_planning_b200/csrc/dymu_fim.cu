@@ -520,14 +520,15 @@ __global__ void k_seed(double* T, size_t slot_stride, uint32_t pitch, uint32_t n
     }
 }
 
-__global__ void k_seed_rows(uint32_t ntx, uint32_t ty0, uint32_t ty1, uint32_t* list0,
+// seeds every tile of the given tile-row ranges (domain-decomposition resume)
+__global__ void k_seed_rows(uint32_t ntx, const uint32_t* tile_rows, uint32_t n_tile_rows, uint32_t* list0,
                             uint32_t* flag0, unsigned long long* key0, unsigned long long* gmin,
                             uint32_t* ctrl)
 {
-    uint32_t n = (ty1 - ty0) * ntx;
+    uint32_t n = n_tile_rows * ntx;
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    uint32_t tile_id = ty0 * ntx + q;
+    uint32_t tile_id = tile_rows[q / ntx] * ntx + q % ntx;
     flag0[tile_id] = kFull;
     key0[tile_id] = 0ull;
     list0[q] = tile_id;
@@ -536,6 +537,26 @@ __global__ void k_seed_rows(uint32_t ntx, uint32_t ty0, uint32_t ty1, uint32_t* 
         ctrl[0] = n;
         gmin[0] = 0ull;
     }
+}
+
+__global__ void k_import_rows_min(double* T, uint32_t pitch, uint32_t nx, uint32_t j0, uint32_t n_rows,
+                                  const double* src, int* changed)
+{
+    size_t total = (size_t)nx * n_rows;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    int any = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride)
+    {
+        uint32_t r = (uint32_t)(k / nx), i = (uint32_t)(k % nx);
+        double v = src[k];
+        double* t = &T[(size_t)(j0 + r) * pitch + i];
+        if (v < *t)
+        {
+            *t = v;
+            any = 1;
+        }
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *changed = 1;
 }
 
 template <int TILE, int MODE> int launch_fim(dymu_ctx* ctx, Params& prm, size_t total_tiles)
@@ -853,17 +874,44 @@ int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_
     return rc;
 }
 
-int dymu_solve_resume(dymu_ctx* ctx, uint32_t j0, uint32_t j1, dymu_solve_stats* stats)
+int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, dymu_solve_stats* stats)
 {
-    if (!ctx || j0 >= j1 || j1 > ctx->ny) return DYMU_ERR_ARG;
+    if (!ctx || !ranges || n_ranges == 0) return DYMU_ERR_ARG;
     if (!ctx->have_cost) DYMU_FAIL(ctx, DYMU_ERR_STATE, "no cost map");
     DYMU_TRY(dymu_internal_refresh_ceff(ctx));
+    // distinct tile rows covered by the ranges
+    uint32_t* h_rows = (uint32_t*)malloc(sizeof(uint32_t) * ctx->nty);
+    uint32_t n_rows = 0;
+    for (uint32_t ty = 0; ty < ctx->nty; ++ty)
+    {
+        bool hit = false;
+        for (uint32_t k = 0; k < n_ranges && !hit; ++k)
+        {
+            uint32_t j0 = ranges[2 * k], j1 = ranges[2 * k + 1];
+            if (j0 >= j1 || j1 > ctx->ny)
+            {
+                free(h_rows);
+                return DYMU_ERR_ARG;
+            }
+            hit = (j0 < (ty + 1) * ctx->tile) && (j1 > ty * ctx->tile);
+        }
+        if (hit) h_rows[n_rows++] = ty;
+    }
     DYMU_TRY(reset_work(ctx, &ctx->work));
-    uint32_t ty0 = j0 / ctx->tile, ty1 = dymu_div_up(j1, ctx->tile);
-    uint32_t ntl = (ty1 - ty0) * ctx->ntx;
-    k_seed_rows<<<dymu_div_up(ntl, 128), 128, 0, ctx->stream>>>(ctx->ntx, ty0, ty1, ctx->work.list[0],
-                                                                ctx->work.flag[0], ctx->work.key[0],
-                                                                ctx->work.gmin, ctx->work.ctrl);
+    int rc = dymu_internal_scratch(ctx, sizeof(uint32_t) * ctx->nty, sizeof(uint32_t) * ctx->nty);
+    if (rc != DYMU_OK)
+    {
+        free(h_rows);
+        return rc;
+    }
+    memcpy(ctx->h_pinned, h_rows, sizeof(uint32_t) * n_rows);
+    free(h_rows);
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, ctx->h_pinned, sizeof(uint32_t) * n_rows,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t ntl = n_rows * ctx->ntx;
+    k_seed_rows<<<dymu_div_up(ntl, 128), 128, 0, ctx->stream>>>(
+        ctx->ntx, (const uint32_t*)ctx->d_scratch, n_rows, ctx->work.list[0], ctx->work.flag[0],
+        ctx->work.key[0], ctx->work.gmin, ctx->work.ctrl);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     dymu_fim_launch L;
@@ -872,9 +920,63 @@ int dymu_solve_resume(dymu_ctx* ctx, uint32_t j0, uint32_t j1, dymu_solve_stats*
     L.mode = 0; L.tile = (int)ctx->tile; L.work = &ctx->work; L.n_initial = ntl; L.band = ctx->fim_band;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
-    int rc = dymu_internal_fim_run(ctx, L, &local);
+    rc = dymu_internal_fim_run(ctx, L, &local);
     if (stats && (rc == DYMU_OK || rc == DYMU_ERR_NOCONV)) stats[0] = local;
     return rc;
+}
+
+int dymu_reset_total_cost(dymu_ctx* ctx)
+{
+    if (!ctx) return DYMU_ERR_ARG;
+    ctx->solved = false;
+    return dymu_internal_fill(ctx, ctx->T, 1.0 / 0.0, (size_t)ctx->pitch * ctx->rows);
+}
+
+int dymu_export_rows(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows, double* dst,
+                     int device_ptr)
+{
+    if (!ctx || !dst || slot >= ctx->n_slots || n_rows == 0 || (uint64_t)j0 + n_rows > ctx->ny)
+        return DYMU_ERR_ARG;
+    const double* src = ctx->T + (size_t)slot * ctx->pitch * ctx->rows + (size_t)j0 * ctx->pitch;
+    DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, ctx->nx * sizeof(double), src, ctx->pitch * sizeof(double),
+                                         ctx->nx * sizeof(double), n_rows,
+                                         device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DYMU_OK;
+}
+
+int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
+                         const double* src, int device_ptr, int* changed)
+{
+    if (!ctx || !src || !changed || slot >= ctx->n_slots || n_rows == 0
+        || (uint64_t)j0 + n_rows > ctx->ny)
+        return DYMU_ERR_ARG;
+    size_t bytes = (size_t)ctx->nx * n_rows * sizeof(double);
+    DYMU_TRY(dymu_internal_scratch(ctx, bytes + 64, device_ptr ? 64 : bytes + 64));
+    int* d_flag = (int*)ctx->d_scratch;
+    const double* d_src = src;
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    if (!device_ptr)
+    {
+        double* stage = (double*)((char*)ctx->d_scratch + 64);
+        memcpy((char*)ctx->h_pinned + 64, src, bytes);
+        DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(stage, (char*)ctx->h_pinned + 64, bytes, cudaMemcpyHostToDevice,
+                                           ctx->stream));
+        d_src = stage;
+    }
+    size_t total = (size_t)ctx->nx * n_rows;
+    int grid = (int)((total + 255) / 256);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    k_import_rows_min<<<grid, 256, 0, ctx->stream>>>(ctx->T + (size_t)slot * ctx->pitch * ctx->rows,
+                                                     ctx->pitch, ctx->nx, j0, n_rows, d_src, d_flag);
+    ctx->launches++;
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    int h = 0;
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *changed = h;
+    return DYMU_OK;
 }
 
 int dymu_stop_threshold(dymu_ctx* ctx, uint32_t slot, uint32_t start_i, uint32_t start_j,

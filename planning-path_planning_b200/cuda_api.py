@@ -63,7 +63,11 @@ _SIG = {
     "dymu_reserve_slots": (C.c_int, [C.c_void_p, C.c_uint32]),
     "dymu_solve_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p,
                                         C.POINTER(SolveStats)]),
-    "dymu_solve_resume": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SolveStats)]),
+    "dymu_solve_resume": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, C.POINTER(SolveStats)]),
+    "dymu_reset_total_cost": (C.c_int, [C.c_void_p]),
+    "dymu_export_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]),
+    "dymu_import_rows_min": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                       C.c_int, C.POINTER(C.c_int)]),
     "dymu_count_reached": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
     "dymu_stop_threshold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp]),
     "dymu_download_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_size_t, C.c_int]),
@@ -254,10 +258,26 @@ class DeviceLayer:
                                                 gj.ctypes.data_as(_u32p), C.byref(st)))
         return st.as_dict()
 
-    def solve_resume(self, j0, j1):
+    def solve_resume(self, ranges):
+        """ranges: iterable of (j0, j1) row ranges whose tiles are re-activated."""
+        r = np.ascontiguousarray(list(ranges), dtype=np.uint32).reshape(-1, 2)
         st = SolveStats()
-        self._chk(self._l.dymu_solve_resume(self._h, j0, j1, C.byref(st)))
+        self._chk(self._l.dymu_solve_resume(self._h, r.ctypes.data_as(_u32p), r.shape[0],
+                                            C.byref(st)))
         return st.as_dict()
+
+    def reset_total_cost(self):
+        self._chk(self._l.dymu_reset_total_cost(self._h))
+
+    def export_rows(self, j0, n_rows, dst_ptr, device_ptr, slot=0):
+        self._chk(self._l.dymu_export_rows(self._h, slot, j0, n_rows, C.c_void_p(dst_ptr),
+                                           int(device_ptr)))
+
+    def import_rows_min(self, j0, n_rows, src_ptr, device_ptr, slot=0):
+        ch = C.c_int()
+        self._chk(self._l.dymu_import_rows_min(self._h, slot, j0, n_rows, C.c_void_p(src_ptr),
+                                               int(device_ptr), C.byref(ch)))
+        return bool(ch.value)
 
     def count_reached(self, slot=0):
         n = C.c_uint64()
