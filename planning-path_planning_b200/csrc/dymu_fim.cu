@@ -364,12 +364,20 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             const int oA = (by * 8 + ly + 1) * P + bx * 8 + lx + 1, oB = oA + 4 * P;
             const double cA = Cs[(by * 8 + ly) * P + bx * 8 + lx], cB = Cs[(by * 8 + ly + 4) * P + bx * 8 + lx];
             const uint32_t my_bit = 1u << warp;
+            // neighbour-block bits (0 where the block sits on the tile edge) and which tile
+            // edges this block touches
+            const uint32_t bitL = bx > 0 ? my_bit >> 1 : 0u, bitR = bx < K::BX - 1 ? my_bit << 1 : 0u;
+            const uint32_t bitU = by > 0 ? my_bit >> 4 : 0u, bitD = by < K::BY - 1 ? my_bit << 4 : 0u;
+            const bool at_edge = !(bitL && bitR && bitU && bitD);
             int it = 0;
-            uint32_t m = dmask[0];
+            uint32_t visits = 0;
+            uint32_t* m_cur = &dmask[0];
+            uint32_t* m_nxt = &dmask[1];
+            uint32_t* m_old = &dmask[2];
+            uint32_t m = *m_cur;
             while (m != 0 && it < p.inner_cap)
             {
-                const int nxt_m = (it + 1) % 3;
-                if (tid == 0) dmask[(it + 2) % 3] = 0;
+                if (tid == 0) *m_old = 0;
                 if (m & my_bit)
                 {
                     const double tA = Ts[oA], lA = Ts[oA - 1], rA = Ts[oA + 1], uA = Ts[oA - P], dA = Ts[oA + P];
@@ -381,21 +389,37 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     if (chB) Ts[oB] = nB;
                     const uint32_t mA = __ballot_sync(0xffffffffu, chA);
                     const uint32_t mB = __ballot_sync(0xffffffffu, chB);
-                    n_visits += 2;
-                    if ((mA | mB) && lane == 0)
+                    const uint32_t mAB = mA | mB;
+                    visits += 2;
+                    if (mAB)
                     {
                         uint32_t bits = my_bit;
-                        if ((mA | mB) & kLeftLanes) { if (bx > 0) bits |= my_bit >> 1; else edge_changed[2] = 1; }
-                        if ((mA | mB) & kRightLanes) { if (bx < K::BX - 1) bits |= my_bit << 1; else edge_changed[3] = 1; }
-                        if (mA & kTopLanes) { if (by > 0) bits |= my_bit >> 4; else edge_changed[0] = 1; }
-                        if (mB & kBottomLanes) { if (by < K::BY - 1) bits |= my_bit << 4; else edge_changed[1] = 1; }
-                        atomicOr(&dmask[nxt_m], bits);
+                        bits |= (mAB & kLeftLanes) ? bitL : 0u;
+                        bits |= (mAB & kRightLanes) ? bitR : 0u;
+                        bits |= (mA & kTopLanes) ? bitU : 0u;
+                        bits |= (mB & kBottomLanes) ? bitD : 0u;
+                        if (lane == 0)
+                        {
+                            atomicOr(m_nxt, bits);
+                            if (at_edge)
+                            {
+                                if ((mAB & kLeftLanes) && !bitL) edge_changed[2] = 1;
+                                if ((mAB & kRightLanes) && !bitR) edge_changed[3] = 1;
+                                if ((mA & kTopLanes) && !bitU) edge_changed[0] = 1;
+                                if ((mB & kBottomLanes) && !bitD) edge_changed[1] = 1;
+                            }
+                        }
                     }
                 }
                 __syncthreads();
                 ++it;
-                m = dmask[it % 3];
+                uint32_t* t_ = m_cur;
+                m_cur = m_nxt;
+                m_nxt = m_old;
+                m_old = t_;
+                m = *m_cur;
             }
+            n_visits += visits;
             const int more = (m != 0);
             if (more && tid == 0) p.dsave[tile_id] = m;
             PC_MARK(pc_sweep)

@@ -10,6 +10,8 @@
 // cell-corner gradients in parallel, the results are exchanged with warp shuffles and every
 // lane carries the identical waypoint state, so there is no divergence; lane 0 stores the
 // waypoint.  Batches of queries run one warp (one CTA) per query.
+#include <limits.h>
+
 #include "dymu_ctx.cuh"
 
 namespace
@@ -77,44 +79,64 @@ __device__ __forceinline__ void grad_node(const PathArgs& a, const Patch& pt, ui
 }
 
 // computeNextGlobalWaypoint, G.cpp:666-714.  Returns false if the cell leaves the grid.
-// (re)loads the shared-memory window so that cells [cx-1, cx+2] x [cy-1, cy+2] are inside
-__device__ __forceinline__ void ensure_patch(const PathArgs& a, Patch& pt, int lane, int cx, int cy)
+constexpr int PATH_THREADS = 256;  // warp 0 walks the path; all 8 warps reload the patch
+
+// Patch reload protocol: the walker (warp 0) publishes the new origin in shared memory and
+// meets the helper warps at a block barrier; everybody loads; a second barrier releases
+// the walker.  x0 = INT_MIN tells the helpers to exit.
+struct PatchCmd
+{
+    int x0, y0;
+};
+
+__device__ __forceinline__ void load_patch(const PathArgs& a, double* pt_t, double* pt_e, int x0, int y0)
+{
+    for (int k = threadIdx.x; k < PATCH * PATCH; k += PATH_THREADS)
+    {
+        int r = k / PATCH, c = k % PATCH;
+        int gx = x0 + c, gy = y0 + r;
+        double tv = DYMU_INF, ev = 0.0;
+        if (gx >= 0 && gy >= 0 && gx < (int)a.nx && gy < (int)a.ny)
+        {
+            tv = __ldcg(a.T + (size_t)gy * a.pitch + gx);
+            ev = a.elev[(size_t)gy * a.pitch + gx];
+        }
+        pt_t[k] = tv;
+        pt_e[k] = ev;
+    }
+}
+
+// makes sure cells [cx-1, cx+2] x [cy-1, cy+2] are inside the shared-memory window
+__device__ __forceinline__ void ensure_patch(const PathArgs& a, Patch& pt, PatchCmd* cmd, int lane, int cx,
+                                             int cy)
 {
     if (pt.valid && cx - 1 >= pt.x0 && cy - 1 >= pt.y0 && cx + 2 < pt.x0 + PATCH && cy + 2 < pt.y0 + PATCH)
         return;
-    __syncwarp();
     pt.x0 = cx - PATCH / 2;
     pt.y0 = cy - PATCH / 2;
     pt.valid = true;
-    for (int r = 0; r < PATCH; ++r)
+    if (lane == 0)
     {
-        int gy = pt.y0 + r;
-        for (int c = lane; c < PATCH; c += 32)
-        {
-            int gx = pt.x0 + c;
-            double tv = DYMU_INF, ev = 0.0;
-            if (gx >= 0 && gy >= 0 && gx < (int)a.nx && gy < (int)a.ny)
-            {
-                tv = __ldcg(a.T + (size_t)gy * a.pitch + gx);
-                ev = a.elev[(size_t)gy * a.pitch + gx];
-            }
-            pt.t[r * PATCH + c] = tv;
-            pt.e[r * PATCH + c] = ev;
-        }
+        cmd->x0 = pt.x0;
+        cmd->y0 = pt.y0;
     }
-    __syncwarp();
+    __syncthreads();  // helpers are parked at the matching barrier
+    load_patch(a, pt.t, pt.e, pt.x0, pt.y0);
+    __syncthreads();
 }
 
-__device__ __forceinline__ bool next_waypoint(const PathArgs& a, Patch& pt, int lane, double wx,
-                                              double wy, double& z, double& dCx, double& dCy,
-                                              double& nx_, double& ny_)
+__device__ __forceinline__ bool next_waypoint(const PathArgs& a, Patch& pt, PatchCmd* cmd, int lane,
+                                              double wx, double wy, double& z, double& dCx,
+                                              double& dCy, double& nx_, double& ny_)
 {
-    double gx = wx / a.gres, gy = wy / a.gres;
+    // x / 1.0 == x exactly: skip the two fp64 divisions for the usual global_res = 1
+    const bool unit = (a.gres == 1.0);
+    double gx = unit ? wx : wx / a.gres, gy = unit ? wy : wy / a.gres;
     if (!(gx >= 0.0) || !(gy >= 0.0) || !(gx < (double)(a.nx - 1)) || !(gy < (double)(a.ny - 1)))
         return false;
     uint32_t cx = (uint32_t)gx, cy = (uint32_t)gy;
     double da = gx - (double)cx, db = gy - (double)cy;
-    ensure_patch(a, pt, lane, (int)cx, (int)cy);
+    ensure_patch(a, pt, cmd, lane, (int)cx, (int)cy);
     // lane c (0..3) owns corner (cx + (c&1), cy + (c>>1)): 0=n00 1=n10 2=n01 3=n11
     int c = lane & 3;
     uint32_t ci = cx + (uint32_t)(c & 1), cj = cy + (uint32_t)(c >> 1);
@@ -144,16 +166,29 @@ __device__ __forceinline__ double dist2d(double ax, double ay, double bx, double
 }
 
 // computeGlobalPath, G.cpp:615-662
-__global__ void __launch_bounds__(32, 1) k_global_path(const PathArgs* args_arr)
+__global__ void __launch_bounds__(PATH_THREADS, 1) k_global_path(const PathArgs* args_arr)
 {
     const PathArgs a = args_arr[blockIdx.x];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     extern __shared__ __align__(16) double path_smem[];
+    __shared__ PatchCmd cmd;
     Patch pt;
     pt.t = path_smem;
     pt.e = path_smem + PATCH * PATCH;
     pt.x0 = pt.y0 = 0;
     pt.valid = false;
+    if (threadIdx.x >= 32)
+    {
+        // helper warps: serve patch reloads until the walker signals the end
+        for (;;)
+        {
+            __syncthreads();
+            const int x0 = cmd.x0, y0 = cmd.y0;
+            if (x0 == INT_MIN) return;
+            load_patch(a, pt.t, pt.e, x0, y0);
+            __syncthreads();
+        }
+    }
     const double sx = a.gres * (double)a.goal_i, sy = a.gres * (double)a.goal_j;
     uint32_t n = 0, status = DYMU_PATH_OK;
     double wx = a.x0, wy = a.y0, z, dCx, dCy, nx_, ny_;
@@ -169,7 +204,7 @@ __global__ void __launch_bounds__(32, 1) k_global_path(const PathArgs* args_arr)
         return true;
     };
 
-    if (!next_waypoint(a, pt, lane, wx, wy, z, dCx, dCy, nx_, ny_)) status = DYMU_PATH_OUTSIDE;
+    if (!next_waypoint(a, pt, &cmd, lane, wx, wy, z, dCx, dCy, nx_, ny_)) status = DYMU_PATH_OUTSIDE;
     else if (isnan(nx_) || isnan(ny_)) status = DYMU_PATH_NAN;
     else
     {
@@ -178,7 +213,7 @@ __global__ void __launch_bounds__(32, 1) k_global_path(const PathArgs* args_arr)
         wy = ny_;
         while (dist2d(wx, wy, sx, sy) > 2.0 * a.gres)
         {
-            if (!next_waypoint(a, pt, lane, wx, wy, z, dCx, dCy, nx_, ny_))
+            if (!next_waypoint(a, pt, &cmd, lane, wx, wy, z, dCx, dCy, nx_, ny_))
             {
                 status = DYMU_PATH_OUTSIDE;
                 break;
@@ -203,7 +238,9 @@ __global__ void __launch_bounds__(32, 1) k_global_path(const PathArgs* args_arr)
     {
         a.result[0] = n;
         a.result[1] = status;
+        cmd.x0 = INT_MIN;  // release the helper warps
     }
+    __syncthreads();
 }
 }  // namespace
 
@@ -235,7 +272,7 @@ int dymu_extract_global_path(dymu_ctx* ctx, uint32_t slot, double x0, double y0,
     const size_t smem = 2 * PATCH * PATCH * sizeof(double);
     DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(k_global_path, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
-    k_global_path<<<1, 32, smem, ctx->stream>>>((const PathArgs*)ctx->d_scratch);
+    k_global_path<<<1, PATH_THREADS, smem, ctx->stream>>>((const PathArgs*)ctx->d_scratch);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     uint32_t* h_res = (uint32_t*)((char*)ctx->h_pinned + sizeof(PathArgs));

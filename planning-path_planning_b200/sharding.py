@@ -94,6 +94,9 @@ class TorchComm:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
+            # NCCL completes on torch's stream; the library reads the rows on its own stream
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
         return from_above, from_below
 
     def any(self, flag):

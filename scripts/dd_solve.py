@@ -1,6 +1,6 @@
 """Domain-decomposed total-cost solve of one large grid across the GPUs of a node
 (BASELINE.json configs[4]).  Launch:  torchrun --nnodes=1 --nproc-per-node N
---master-addr 127.0.0.1 scripts/dd_solve.py --n 16384 [--verify]"""
+--master-addr 127.0.0.1 scripts/dd_solve.py --size 16384 [--verify]"""
 import argparse
 import json
 import os
@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dymu_b200
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=16384)
+ap.add_argument("--size", dest="n", type=int, default=16384)
 ap.add_argument("--base", type=int, default=4096, help="edge of the periodic fBm cost tile")
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
