@@ -544,6 +544,21 @@ __global__ void k_seed(double* T, size_t slot_stride, uint32_t pitch, uint32_t n
     }
 }
 
+__global__ void k_seed_all(uint32_t n, uint32_t* list0, uint32_t* flag0, unsigned long long* key0,
+                           unsigned long long* gmin, uint32_t* ctrl)
+{
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    list0[q] = q;
+    flag0[q] = kFull;
+    key0[q] = 0ull;
+    if (q == 0)
+    {
+        ctrl[0] = n;
+        gmin[0] = 0ull;
+    }
+}
+
 // seeds every tile of the given tile-row ranges (domain-decomposition resume)
 __global__ void k_seed_rows(uint32_t ntx, const uint32_t* tile_rows, uint32_t n_tile_rows, uint32_t* list0,
                             uint32_t* flag0, unsigned long long* key0, unsigned long long* gmin,
@@ -666,9 +681,28 @@ int dymu_internal_fim_configure(dymu_ctx* ctx)
     return DYMU_OK;
 }
 
-// Runs the persistent kernel on a prepared work list and collects statistics.
+int dymu_internal_fim_reset(dymu_ctx* ctx, dymu_fim_work* w);
+
+// Seeds the work lists, runs the persistent kernel and collects statistics.
 int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_stats* stats)
 {
+    if (L.tile != 32) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unsupported tile edge %d", L.tile);
+    {
+        dymu_fim_work* w0 = L.work;
+        DYMU_TRY(dymu_internal_fim_reset(ctx, w0));
+        if (L.seed_kind == 0)
+            k_seed<<<dymu_div_up(L.n_initial, 128), 128, 0, ctx->stream>>>(
+                L.T, L.slot_stride, L.pitch, L.ntx, L.nty, L.tile, L.seed_data, L.n_initial, w0->list[0],
+                w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
+        else if (L.seed_kind == 1)
+            k_seed_rows<<<dymu_div_up(L.n_initial * L.ntx, 128), 128, 0, ctx->stream>>>(
+                L.ntx, L.seed_data, L.n_initial, w0->list[0], w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
+        else
+            k_seed_all<<<dymu_div_up(L.ntx * L.nty, 128), 128, 0, ctx->stream>>>(
+                L.ntx * L.nty, w0->list[0], w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
+        ctx->launches++;
+        DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    }
     dymu_fim_work* w = L.work;
     Params prm;
     prm.T = L.T;
@@ -723,7 +757,6 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     size_t total_tiles = (size_t)L.ntx * L.nty * L.nprob;
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     int rc;
-    if (L.tile != 32) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unsupported tile edge %d", L.tile);
     rc = (L.mode == 0) ? launch_fim<32, 0>(ctx, prm, total_tiles) : launch_fim<32, 1>(ctx, prm, total_tiles);
     DYMU_TRY(rc);
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
@@ -866,7 +899,6 @@ int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_
     // resetTotalCostMap, G.cpp:473-485 (whole plane instead of the propagated-node list)
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     DYMU_TRY(dymu_internal_fill(ctx, ctx->T, 1.0 / 0.0, n * n_goals));
-    DYMU_TRY(reset_work(ctx, &ctx->work));
     DYMU_TRY(dymu_internal_scratch(ctx, (size_t)n_goals * 8, (size_t)n_goals * 8));
     uint32_t* h_goals = (uint32_t*)ctx->h_pinned;
     for (uint32_t q = 0; q < n_goals; ++q)
@@ -876,16 +908,11 @@ int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_
     }
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, h_goals, (size_t)n_goals * 8,
                                        cudaMemcpyHostToDevice, ctx->stream));
-    k_seed<<<dymu_div_up(n_goals, 128), 128, 0, ctx->stream>>>(
-        ctx->T, n, ctx->pitch, ctx->ntx, ctx->nty, (int)ctx->tile, (const uint32_t*)ctx->d_scratch,
-        n_goals, ctx->work.list[0], ctx->work.flag[0], ctx->work.key[0], ctx->work.gmin,
-        ctx->work.ctrl);
-    ctx->launches++;
-    DYMU_CUDA_TRY(ctx, cudaGetLastError());
     dymu_fim_launch L;
     L.T = ctx->T; L.slot_stride = n; L.C = ctx->ceff; L.pitch = ctx->pitch; L.rows = ctx->rows;
     L.ntx = ctx->ntx; L.nty = ctx->nty; L.nprob = n_goals; L.mode = 0; L.tile = (int)ctx->tile;
     L.work = &ctx->work; L.n_initial = n_goals; L.band = ctx->fim_band;
+    L.seed_kind = 0; L.seed_data = (const uint32_t*)ctx->d_scratch;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     int rc = dymu_internal_fim_run(ctx, L, &local);
@@ -921,7 +948,6 @@ int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, 
         }
         if (hit) h_rows[n_rows++] = ty;
     }
-    DYMU_TRY(reset_work(ctx, &ctx->work));
     int rc = dymu_internal_scratch(ctx, sizeof(uint32_t) * ctx->nty, sizeof(uint32_t) * ctx->nty);
     if (rc != DYMU_OK)
     {
@@ -932,16 +958,11 @@ int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, 
     free(h_rows);
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, ctx->h_pinned, sizeof(uint32_t) * n_rows,
                                        cudaMemcpyHostToDevice, ctx->stream));
-    uint32_t ntl = n_rows * ctx->ntx;
-    k_seed_rows<<<dymu_div_up(ntl, 128), 128, 0, ctx->stream>>>(
-        ctx->ntx, (const uint32_t*)ctx->d_scratch, n_rows, ctx->work.list[0], ctx->work.flag[0],
-        ctx->work.key[0], ctx->work.gmin, ctx->work.ctrl);
-    ctx->launches++;
-    DYMU_CUDA_TRY(ctx, cudaGetLastError());
     dymu_fim_launch L;
     L.T = ctx->T; L.slot_stride = (size_t)ctx->pitch * ctx->rows; L.C = ctx->ceff;
     L.pitch = ctx->pitch; L.rows = ctx->rows; L.ntx = ctx->ntx; L.nty = ctx->nty; L.nprob = 1;
-    L.mode = 0; L.tile = (int)ctx->tile; L.work = &ctx->work; L.n_initial = ntl; L.band = ctx->fim_band;
+    L.mode = 0; L.tile = (int)ctx->tile; L.work = &ctx->work; L.n_initial = n_rows; L.band = ctx->fim_band;
+    L.seed_kind = 1; L.seed_data = (const uint32_t*)ctx->d_scratch;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     rc = dymu_internal_fim_run(ctx, L, &local);

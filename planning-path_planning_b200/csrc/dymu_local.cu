@@ -265,21 +265,6 @@ __global__ void k_mark_entered_risk(LocalView v, uint8_t* entered)
     }
 }
 
-__global__ void k_all_tiles(uint32_t n, uint32_t* list0, uint32_t* flag0, unsigned long long* key0,
-                            unsigned long long* gmin, uint32_t* ctrl)
-{
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    list0[q] = q;
-    flag0[q] = 16u;  // kFull
-    key0[q] = 0ull;
-    if (q == 0)
-    {
-        ctrl[0] = n;
-        gmin[0] = 0ull;
-    }
-}
-
 // ---------------------------------------------------------------------------------
 // local propagation in the reference's pop order
 // ---------------------------------------------------------------------------------
@@ -944,17 +929,13 @@ int dymu_local_expand_risk(dymu_ctx* ctx, double risk_distance, dymu_solve_stats
                                                  l.rows, l.w);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
-    DYMU_TRY(dymu_internal_fim_reset(ctx, &l.work));
     uint32_t nt = l.pitch / ctx->tile;
-    k_all_tiles<<<dymu_div_up(nt * nt, 128), 128, 0, ctx->stream>>>(
-        nt * nt, l.work.list[0], l.work.flag[0], l.work.key[0], l.work.gmin, l.work.ctrl);
-    ctx->launches++;
-    DYMU_CUDA_TRY(ctx, cudaGetLastError());
     dymu_fim_launch L;
     L.T = l.risk; L.slot_stride = n; L.C = l.crisk; L.pitch = l.pitch; L.rows = l.rows;
     L.ntx = nt; L.nty = nt; L.nprob = 1; L.mode = 1; L.tile = (int)ctx->tile; L.work = &l.work;
     L.n_initial = nt * nt;
     L.band = 1.0 / 0.0;  // small window: plain FIM
+    L.seed_kind = 2; L.seed_data = nullptr;
     DYMU_TRY(dymu_internal_fim_run(ctx, L, stats));
     k_mark_entered_risk<<<grid, 256, 0, ctx->stream>>>(make_view(ctx), l.entered);
     ctx->launches++;
