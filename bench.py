@@ -48,6 +48,12 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="plan4096", choices=["plan4096", "queries2048"],
+                    help="plan4096 = BASELINE configs[2] (default, the headline); queries2048 = "
+                         "configs[3]: batches of independent goal queries on one shared 2048^2 map, "
+                         "sharded across the ranks")
+    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--seed", type=int, default=20261018)
     return ap.parse_args()
 
@@ -406,6 +412,19 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    # the streaming (HBM-bound) stencil kernels of the same path, timed once each
+    try:
+        sm = dev.time_stencils()
+        cells, pcells = float(n * n), float(pitch * rows)
+        spec = [("k_fill_f64 (total-cost reset)", sm[0], 8 * cells),
+                ("k_ceff (C_eff build)", sm[1], 33 * pcells),
+                ("k_readback (inf -> -1)", sm[2], 16 * cells),
+                ("k_set_cost_map (obstacle mask)", sm[3], 8 * cells)]
+        line["stencils"] = {nm: {"ms": ms_, "algorithmic_bytes": b, "gbs": b / (ms_ * 1e-3) / 1e9,
+                                 "frac_of_measured_peak": b / (ms_ * 1e-3) / 1e9 / peak}
+                            for nm, ms_, b in spec if ms_ > 0}
+    except Exception as e:  # timing helper is informational
+        line["stencils"] = {"error": str(e)}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_leg(pkg, elev, terr, lut, slopes, locs, n)
     print(json.dumps(line))
@@ -414,6 +433,77 @@ def run_b200(args):
     return 0
 
 
+def run_queries(args):
+    """configs[3]: `--queries` independent goal queries (full solve + path each) on one shared
+    2048x2048 map, block-sharded over the ranks (no data-path collective), `--batch` goals per
+    launch.  One JSON line; a step = this rank's whole share."""
+    import torch
+    import dymu_b200
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    pkg = dymu_b200.load()
+    syn, sh = pkg.synthetic, pkg.sharding
+    n = 2048
+    elev, terr, lut, slopes, locs = build_workload(pkg, n, args.seed)
+    dev = pkg.cuda_api.DeviceLayer(n, n, 1.0, 0.1, device=local_rank)
+    dev.compute_cost_map(lut, slopes, len(locs), elev, terr)
+    ob = dev.download_plane_u8("obstacle")
+    rng_g, rng_s = np.random.default_rng(11), np.random.default_rng(13)
+    goals = [syn.free_interior_cell_near(ob, int(rng_g.uniform(0.03, 0.97) * n),
+                                         int(rng_g.uniform(0.03, 0.97) * n)) for _ in range(args.queries)]
+    starts = [syn.free_interior_cell_near(ob, int(rng_s.uniform(0.03, 0.97) * n),
+                                          int(rng_s.uniform(0.03, 0.97) * n)) for _ in range(args.queries)]
+    mine = list(sh.shard_queries(args.queries, world, rank))
+    B = max(1, min(args.batch, len(mine)))
+    dev.reserve_slots(B)
+
+    def share():
+        nwp = 0
+        for lo in range(0, len(mine), B):
+            idx = mine[lo:lo + B]
+            dev.solve_total_cost([goals[q] for q in idx])
+            paths, _ = dev.extract_global_path_batch(
+                list(range(len(idx))), [[float(starts[q][0]), float(starts[q][1])] for q in idx], 0.4,
+                [goals[q] for q in idx], cap=1 << 14)
+            nwp += sum(len(w) for w in paths)
+        return nwp
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        share()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    launches0 = dev.launches
+    dev.event_record(0)
+    for _ in range(args.steps):
+        nwp = share()
+    dev.event_record(1)
+    ms = dev.event_elapsed_ms(0, 1)
+    launches = dev.launches - launches0
+    if distributed:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": args.queries * args.steps / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "configs[3]: %d independent goal queries (solve + path) on one shared "
+                                   "2048x2048 map, %d goals per launch, block-sharded over %d GPU(s)"
+                                   % (args.queries, B, world), "seed": args.seed},
+            "gpu_launches": int(launches), "waypoints_last_share": nwp}))
+    return 0
+
+
 if __name__ == "__main__":
     a = parse_args()
-    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))
+    if a.impl == "reference":
+        sys.exit(run_reference(a))
+    sys.exit(run_queries(a) if a.workload == "queries2048" else run_b200(a))

@@ -93,6 +93,12 @@ int dymu_event_elapsed_ms(dymu_ctx* ctx, int a, int b, float* ms);
  * pseudo-random positive normal doubles; *mismatches must come back 0. */
 int dymu_selftest_sqrt(dymu_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches,
                        double* first_bad);
+/* Times the streaming stencil kernels of the path once each on the resident planes (CUDA
+ * events on the context's stream).  ms[0..5] = total-cost reset (k_fill_f64), C_eff build
+ * (k_ceff), read-back transform (k_readback), setCostMap mask (k_set_cost_map), slope +
+ * nominal cost (k_slope_nominal; -1 if computeCostMap was never called), smoothing
+ * (k_smooth_cost on a scratch copy).  All are idempotent on the context's state. */
+int dymu_time_stencils(dymu_ctx* ctx, float ms[6]);
 /* Tile geometry of the solver: tile edge (cells), padded pitch (doubles per row). */
 int dymu_geometry(const dymu_ctx* ctx, uint32_t* tile, uint32_t* pitch, uint32_t* rows);
 
@@ -181,6 +187,13 @@ int dymu_count_leq(dymu_ctx* ctx, uint32_t slot, double threshold, uint64_t* n);
 int dymu_extract_global_path(dymu_ctx* ctx, uint32_t slot, double x0, double y0, double tau,
                              uint32_t goal_i, uint32_t goal_j, double* out, uint32_t cap,
                              uint32_t* n_out, int* status);
+
+/* Batched variant: query q descends on slot slots[q] from (xy0[2q], xy0[2q+1]) to goal
+ * (goal_ij[2q], goal_ij[2q+1]); one CTA per query, all in one launch.  out holds n*cap*5
+ * doubles (query q at out + q*cap*5); n_out / status hold n entries. */
+int dymu_extract_global_path_batch(dymu_ctx* ctx, uint32_t n, const uint32_t* slots,
+                                   const double* xy0, double tau, const uint32_t* goal_ij,
+                                   double* out, uint32_t cap, uint32_t* n_out, int* status);
 
 /* ---- local layer --------------------------------------------------------------------- */
 /* The local layer (localNode, H.hpp:42-67) is a dense window of wg x wg global

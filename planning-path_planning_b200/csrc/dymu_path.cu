@@ -289,4 +289,57 @@ int dymu_extract_global_path(dymu_ctx* ctx, uint32_t slot, double x0, double y0,
     return DYMU_OK;
 }
 
+int dymu_extract_global_path_batch(dymu_ctx* ctx, uint32_t n, const uint32_t* slots,
+                                   const double* xy0, double tau, const uint32_t* goal_ij,
+                                   double* out, uint32_t cap, uint32_t* n_out, int* status)
+{
+    if (!ctx || !slots || !xy0 || !goal_ij || !out || !n_out || !status || n == 0 || cap == 0)
+        return DYMU_ERR_ARG;
+    for (uint32_t q = 0; q < n; ++q)
+        if (slots[q] >= ctx->n_slots || goal_ij[2 * q] >= ctx->nx || goal_ij[2 * q + 1] >= ctx->ny)
+            return DYMU_ERR_ARG;
+    const size_t hdr = (((size_t)n * (sizeof(PathArgs) + 8)) + 255) & ~(size_t)255;
+    const size_t out_bytes = (size_t)n * cap * 5 * sizeof(double);
+    DYMU_TRY(dymu_internal_scratch(ctx, hdr + out_bytes, hdr));
+    PathArgs* h_args = (PathArgs*)ctx->h_pinned;
+    char* d_base = (char*)ctx->d_scratch;
+    uint32_t* d_res = (uint32_t*)(d_base + (size_t)n * sizeof(PathArgs));
+    for (uint32_t q = 0; q < n; ++q)
+    {
+        PathArgs a;
+        a.T = ctx->T + (size_t)slots[q] * ctx->pitch * ctx->rows;
+        a.elev = ctx->elev;
+        a.pitch = ctx->pitch; a.nx = ctx->nx; a.ny = ctx->ny;
+        a.gres = ctx->gres; a.tau = tau; a.x0 = xy0[2 * q]; a.y0 = xy0[2 * q + 1];
+        a.goal_i = goal_ij[2 * q]; a.goal_j = goal_ij[2 * q + 1];
+        a.out = (double*)(d_base + hdr) + (size_t)q * cap * 5;
+        a.cap = cap;
+        a.result = d_res + 2 * q;
+        h_args[q] = a;
+    }
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(d_base, h_args, (size_t)n * sizeof(PathArgs), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    const size_t smem = 2 * PATCH * PATCH * sizeof(double);
+    DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(k_global_path, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+    k_global_path<<<n, PATH_THREADS, smem, ctx->stream>>>((const PathArgs*)d_base);
+    ctx->launches++;
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    uint32_t* h_res = (uint32_t*)((char*)ctx->h_pinned + (size_t)n * sizeof(PathArgs));
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h_res, d_res, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t q = 0; q < n; ++q)
+    {
+        n_out[q] = h_res[2 * q];
+        status[q] = (int)h_res[2 * q + 1];
+        if (n_out[q])
+            DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(out + (size_t)q * cap * 5,
+                                               (double*)(d_base + hdr) + (size_t)q * cap * 5,
+                                               (size_t)n_out[q] * 5 * sizeof(double), cudaMemcpyDeviceToHost,
+                                               ctx->stream));
+    }
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DYMU_OK;
+}
+
 }  // extern "C"

@@ -36,17 +36,29 @@ __global__ void k_set_cost_map(const double* __restrict__ cost, uint8_t* __restr
                                double* __restrict__ traff, double* __restrict__ haz,
                                uint32_t pitch, uint32_t nx, uint32_t ny)
 {
-    size_t total = (size_t)nx * ny;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride)
+    // the padded plane is walked as double2 (pitch is a multiple of 32 doubles, rows 256 B
+    // aligned); padding columns/rows are skipped by the bounds test
+    const size_t total2 = (size_t)pitch * ny / 2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t pitch2 = pitch / 2;
+    const double2* cost2 = reinterpret_cast<const double2*>(cost);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total2; k += stride)
     {
-        uint32_t j = (uint32_t)(k / nx), i = (uint32_t)(k % nx);
-        size_t q = (size_t)j * pitch + i;
-        if (cost[q] <= 0)
+        const uint32_t i = (uint32_t)(k % pitch2) * 2;
+        if (i >= nx) continue;
+        const double2 c = cost2[k];
+        const size_t q = 2 * k;
+        if (c.x <= 0)
         {
             obst[q] = 1;
             traff[q] = 0.0;
             haz[q] = 1.0;
+        }
+        if (i + 1 < nx && c.y <= 0)
+        {
+            obst[q + 1] = 1;
+            traff[q + 1] = 0.0;
+            haz[q + 1] = 1.0;
         }
     }
 }
@@ -682,6 +694,45 @@ int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, cons
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // cost_lut/slopes are caller memory
     ctx->have_cost = true;
     ctx->ceff_dirty = true;
+    return DYMU_OK;
+}
+
+int dymu_time_stencils(dymu_ctx* ctx, float ms[6])
+{
+    if (!ctx || !ms) return DYMU_ERR_ARG;
+    for (int k = 0; k < 6; ++k) ms[k] = -1.0f;
+    size_t n = (size_t)ctx->nx * ctx->ny, np = (size_t)ctx->pitch * ctx->rows;
+    DYMU_TRY(ensure_stage(ctx));
+    auto tick = [&](cudaEvent_t e) { return cudaEventRecord(e, ctx->stream); };
+    auto lap = [&](int k) -> int {
+        DYMU_CUDA_TRY(ctx, tick(ctx->ev1));
+        DYMU_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+        DYMU_CUDA_TRY(ctx, cudaEventElapsedTime(&ms[k], ctx->ev0, ctx->ev1));
+        return DYMU_OK;
+    };
+    // warm-up + timed pass of each kernel; d_stage doubles as the scratch output
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        DYMU_CUDA_TRY(ctx, tick(ctx->ev0));
+        k_fill_f64<<<stream_grid(ctx, n / 2 + 1), kThreads, 0, ctx->stream>>>(ctx->d_stage, 0.0, n);
+        DYMU_TRY(lap(0));
+        DYMU_CUDA_TRY(ctx, tick(ctx->ev0));
+        k_ceff<<<stream_grid(ctx, np), kThreads, 0, ctx->stream>>>(ctx->cost, ctx->haz, ctx->traff, ctx->obst,
+                                                                ctx->ceff, ctx->gres, ctx->pitch, ctx->rows,
+                                                                ctx->nx, ctx->ny);
+        DYMU_TRY(lap(1));
+        DYMU_CUDA_TRY(ctx, tick(ctx->ev0));
+        k_readback<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->T, ctx->haz, ctx->traff, ctx->obst,
+                                                                   ctx->d_stage, DYMU_XFORM_INF_TO_MINUS1,
+                                                                   ctx->pitch, ctx->nx, ctx->ny);
+        DYMU_TRY(lap(2));
+        DYMU_CUDA_TRY(ctx, tick(ctx->ev0));
+        k_set_cost_map<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->cost, ctx->obst, ctx->traff,
+                                                                       ctx->haz, ctx->pitch, ctx->nx, ctx->ny);
+        DYMU_TRY(lap(3));
+        ctx->launches += 4;
+    }
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
     return DYMU_OK;
 }
 

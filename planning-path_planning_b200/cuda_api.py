@@ -44,6 +44,7 @@ _SIG = {
     "dymu_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "dymu_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "dymu_selftest_sqrt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), _dp]),
+    "dymu_time_stencils": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "dymu_geometry": (C.c_int, [C.c_void_p, _u32p, _u32p, _u32p]),
     "dymu_upload_plane": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t]),
     "dymu_download_plane": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t, C.c_int]),
@@ -77,6 +78,8 @@ _SIG = {
     "dymu_extract_global_path": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.c_double,
                                            C.c_double, C.c_uint32, C.c_uint32, _dp, C.c_uint32,
                                            _u32p, C.POINTER(C.c_int)]),
+    "dymu_extract_global_path_batch": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _dp, C.c_double, _u32p,
+                                                 _dp, C.c_uint32, _u32p, C.POINTER(C.c_int)]),
     "dymu_local_create": (C.c_int, [C.c_void_p, C.c_uint32]),
     "dymu_local_anchor": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "dymu_local_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _u32p,
@@ -186,6 +189,11 @@ class DeviceLayer:
         bad, first = C.c_uint64(), C.c_double()
         self._chk(self._l.dymu_selftest_sqrt(self._h, n, seed, C.byref(bad), C.byref(first)))
         return int(bad.value), first.value
+
+    def time_stencils(self):
+        ms = (C.c_float * 6)()
+        self._chk(self._l.dymu_time_stencils(self._h, ms))
+        return [float(v) for v in ms]
 
     def geometry(self):
         t, p, r = C.c_uint32(), C.c_uint32(), C.c_uint32()
@@ -321,6 +329,21 @@ class DeviceLayer:
                                                    out.ctypes.data_as(_dp), cap, C.byref(n),
                                                    C.byref(status)))
         return out[:n.value].copy(), status.value
+
+    def extract_global_path_batch(self, slots, starts_xy, tau, goals_ij, cap=1 << 15):
+        """One launch for many queries.  Returns (list of (n_q,5) arrays, list of status)."""
+        sl = np.ascontiguousarray(slots, dtype=np.uint32)
+        xy = _f64(starts_xy).reshape(-1, 2)
+        g = np.ascontiguousarray(goals_ij, dtype=np.uint32).reshape(-1, 2)
+        n = sl.size
+        out = np.empty((n, cap, 5), dtype=np.float64)
+        n_out = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        self._chk(self._l.dymu_extract_global_path_batch(
+            self._h, n, sl.ctypes.data_as(_u32p), xy.ctypes.data_as(_dp), tau, g.ctypes.data_as(_u32p),
+            out.ctypes.data_as(_dp), cap, n_out.ctypes.data_as(_u32p),
+            status.ctypes.data_as(C.POINTER(C.c_int))))
+        return [out[q, :n_out[q]].copy() for q in range(n)], [int(v) for v in status]
 
     # local layer
     def local_create(self, wg):

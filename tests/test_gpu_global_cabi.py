@@ -95,6 +95,12 @@ def test_batched_goals_share_one_launch(pkg, oracle_mod):
     goals = [pkg.synthetic.free_interior_cell_near(ob, x, y) for x, y in
              ((30, 30), (120, 40), (80, 80), (40, 130))]
     dev.solve_total_cost(goals)
+    starts = [[20.0, 140.0], [100.0, 100.0], [30.0, 30.0], [140.0, 25.0]]
+    paths, status = dev.extract_global_path_batch([0, 1, 2, 3], starts, 0.4, goals)
+    for q in range(4):
+        single, st1 = dev.extract_global_path(starts[q][0], starts[q][1], 0.4, goals[q][0], goals[q][1],
+                                              slot=q)
+        assert status[q] == st1 and np.array_equal(paths[q], single, equal_nan=True)
     for q, (gi, gj) in enumerate(goals):
         po = oracle_mod.Port(1.0, 1.5, 2.0, 1)
         po.initGlobalLayer(1.0, 0.1, nx, ny)
