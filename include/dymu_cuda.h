@@ -123,8 +123,10 @@ int dymu_set_cost_map(dymu_ctx* ctx, const double* host, size_t ld);
 /* computeCostMap, G.cpp:145-308: slope (G.cpp:186-210), nominal cost from the
  * [terrain][locomotion][slope] table incl. obstacle marking (G.cpp:217-293),
  * 5-point smoothing seeded with the previous cost (G.cpp:297-308).
- * elevation/terrain may be NULL if already resident (terrain plane: see
- * dymu_upload_terrain). */
+ * elevation/terrain may be NULL if already resident: a terrain map staged by
+ * dymu_upload_terrain is consumed by the next call; after that the terrain classes stay in
+ * HBM, so a call with both NULL rebuilds the cost map from a new table alone (the
+ * updateCost -> computeCostMap loop of CoRa, G.cpp:956-993, without re-sending the DEM). */
 int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, const double* slopes,
                           int n_slopes, int n_locs, const double* elevation, size_t ld_e,
                           const double* terrain, size_t ld_t);

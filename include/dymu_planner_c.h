@@ -111,6 +111,25 @@ double dymu_planner_get_remaining_total_cost(dymu_planner* p);
 /* Per-node taps through getGlobalNode(i,j) (G.cpp:313-317); `out` holds
  * NY*NX doubles (booleans/enums as 0/1). */
 int dymu_planner_get_node_field(dymu_planner* p, int field, double* out);
+/* ---- CoRa: cost ratio updating after traverse, G.cpp:895-1038 ---- */
+/* initCoRaMethod, G.cpp:895-922 */
+int dymu_planner_cora_init(dymu_planner* p, int num_terrains, int num_criteria, const double* weights,
+                           int n_weights);
+/* getTerrain, G.cpp:941-950 (position in world coordinates) */
+int dymu_planner_get_terrain(dymu_planner* p, double x, double y);
+/* fillTerrainInfo, G.cpp:926-938 */
+int dymu_planner_fill_terrain_info(dymu_planner* p, int terrain_id, const double* data, int n);
+/* updateCost, G.cpp:956-993.  Returns the table length; writes min(len, cap) entries. */
+int dymu_planner_update_cost(dymu_planner* p, double* lut, int cap);
+/* computeCostRatio, G.cpp:999-1038.  Returns the number of ratios. */
+int dymu_planner_compute_cost_ratio(dymu_planner* p, double* ratios, int cap);
+/* Re-run computeCostMap (G.cpp:145-181) with the planner's current public cost_lutable and
+ * the slope values / locomotion modes / maps of the last dymu_planner_compute_cost_map call:
+ * the step a CoRa caller performs after updateCost.  The reference build re-sends the maps it
+ * kept on the host; the B200 build rebuilds from the planes resident in HBM
+ * (DyMuPathPlanner::recomputeCostMap). */
+int dymu_planner_recompute_cost_map(dymu_planner* p);
+
 /* seconds spent inside the last call of the given kind (wrapper-side
  * steady_clock around the forwarded method; conversions excluded) */
 double dymu_planner_last_call_seconds(dymu_planner* p);

@@ -25,6 +25,12 @@ struct dymu_planner
     DyMuPathPlanner* impl;
     unsigned nx, ny;
     double last_seconds;
+    // arguments of the last computeCostMap, for dymu_planner_recompute_cost_map
+    std::vector<double> slopes;
+    std::vector<std::string> locs;
+#ifdef DYMU_CAPI_REFERENCE
+    std::vector<std::vector<double>> elevation, terrain;
+#endif
 };
 
 namespace
@@ -162,8 +168,67 @@ int dymu_planner_compute_cost_map(dymu_planner* p, const double* cost_data, int 
     }
     std::vector<std::vector<double>> e = to_nested(elevation, ny, nx);
     std::vector<std::vector<double>> t = to_nested(terrain, ny, nx);
+    p->slopes = slopes;
+    p->locs = locs;
+#ifdef DYMU_CAPI_REFERENCE
+    p->elevation = e;
+    p->terrain = t;
+#endif
     Stopwatch sw(&p->last_seconds);
     return p->impl->computeCostMap(lut, slopes, locs, e, t) ? 1 : 0;
+}
+
+int dymu_planner_recompute_cost_map(dymu_planner* p)
+{
+    if (!p) return -1;
+    Stopwatch sw(&p->last_seconds);
+#ifdef DYMU_CAPI_REFERENCE
+    if (p->elevation.empty()) return 0;
+    return p->impl->computeCostMap(p->impl->cost_lutable, p->slopes, p->locs, p->elevation, p->terrain) ? 1 : 0;
+#else
+    return p->impl->recomputeCostMap(false) ? 1 : 0;
+#endif
+}
+
+int dymu_planner_cora_init(dymu_planner* p, int num_terrains, int num_criteria, const double* weights,
+                           int n_weights)
+{
+    if (!p || n_weights < 0) return -1;
+    return p->impl->initCoRaMethod(num_terrains, num_criteria,
+                                   std::vector<double>(weights, weights + n_weights)) ? 1 : 0;
+}
+
+int dymu_planner_get_terrain(dymu_planner* p, double x, double y)
+{
+    if (!p) return -1;
+    base::samples::RigidBodyState rbs;
+    rbs.position[0] = x;
+    rbs.position[1] = y;
+    return p->impl->getTerrain(rbs);
+}
+
+int dymu_planner_fill_terrain_info(dymu_planner* p, int terrain_id, const double* data, int n)
+{
+    if (!p || n < 0) return -1;
+    CoutSilencer quiet;
+    return p->impl->fillTerrainInfo(terrain_id, std::vector<double>(data, data + n)) ? 1 : 0;
+}
+
+int dymu_planner_update_cost(dymu_planner* p, double* lut, int cap)
+{
+    if (!p) return -1;
+    CoutSilencer quiet;
+    std::vector<double> v = p->impl->updateCost();
+    for (int k = 0; k < (int)v.size() && k < cap; ++k) lut[k] = v[k];
+    return (int)v.size();
+}
+
+int dymu_planner_compute_cost_ratio(dymu_planner* p, double* ratios, int cap)
+{
+    if (!p) return -1;
+    std::vector<double> v = p->impl->computeCostRatio();
+    for (int k = 0; k < (int)v.size() && k < cap; ++k) ratios[k] = v[k];
+    return (int)v.size();
 }
 
 int dymu_planner_set_goal(dymu_planner* p, double x, double y, double heading)

@@ -88,7 +88,8 @@ __global__ void k_slope_nominal(const double* __restrict__ elev,
         // terrain, G.cpp:162-165
         uint32_t terr;
         if ((i == 0) || (j == 0) || (i == nx - 1) || (j == ny - 1)) terr = 0;
-        else terr = (uint32_t)terrain_in[(size_t)j * ld_t + i];
+        else if (terrain_in) terr = (uint32_t)terrain_in[(size_t)j * ld_t + i];
+        else terr = terrain[q];  // LUT-only rebuild: classes already resident
         terrain[q] = terr;
         // slope, G.cpp:186-210 (nb4List[1]=(i-1,j), [2]=(i+1,j), [0]=(i,j-1), [3]=(i,j+1))
         double e = elev[q], dx, dy;
@@ -519,6 +520,7 @@ static int download_f64(dymu_ctx* ctx, const double* d, double* host, size_t ld,
     else
     {
         DYMU_TRY(ensure_stage(ctx));
+        ctx->terrain_staged = false;  // the staging plane is about to be overwritten
         size_t n = (size_t)ctx->nx * ctx->ny;
         k_readback<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(
             d, ctx->haz, ctx->traff, ctx->obst, ctx->d_stage, xform, ctx->pitch, ctx->nx, ctx->ny);
@@ -646,6 +648,7 @@ int dymu_upload_terrain(dymu_ctx* ctx, const double* terrain, size_t ld)
     DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_stage, ctx->nx * sizeof(double), terrain,
                                          ld * sizeof(double), ctx->nx * sizeof(double), ctx->ny,
                                          cudaMemcpyHostToDevice, ctx->stream));
+    ctx->terrain_staged = true;
     return DYMU_OK;
 }
 
@@ -663,8 +666,9 @@ int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, cons
                                              ctx->ny, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (terrain) DYMU_TRY(dymu_upload_terrain(ctx, terrain, ld_t));
-    else if (ctx->stage_elems < (size_t)ctx->nx * ctx->ny)
+    if (!ctx->terrain_staged && !ctx->have_terrain)
         DYMU_FAIL(ctx, DYMU_ERR_STATE, "terrain map was never uploaded");
+    const double* terrain_src = ctx->terrain_staged ? ctx->d_stage : nullptr;
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_slopes) cudaFree(ctx->d_slopes);
     ctx->d_lut = ctx->d_slopes = nullptr;
@@ -682,7 +686,7 @@ int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, cons
         if (cost_lut[q] > Cmax) Cmax = cost_lut[q];
     size_t n = (size_t)ctx->nx * ctx->ny;
     k_slope_nominal<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(
-        ctx->elev, ctx->d_stage, ctx->nx, ctx->d_lut, ctx->d_slopes, n_slopes, n_locs, n_lut, Cmax,
+        ctx->elev, terrain_src, ctx->nx, ctx->d_lut, ctx->d_slopes, n_slopes, n_locs, n_lut, Cmax,
         ctx->gres, ctx->slope, ctx->raw, ctx->terrain, ctx->obst, ctx->locmode, ctx->traff,
         ctx->haz, ctx->pitch, ctx->nx, ctx->ny);
     ctx->launches++;
@@ -692,6 +696,8 @@ int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, cons
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // cost_lut/slopes are caller memory
+    ctx->terrain_staged = false;
+    ctx->have_terrain = true;
     ctx->have_cost = true;
     ctx->ceff_dirty = true;
     return DYMU_OK;
@@ -703,6 +709,7 @@ int dymu_time_stencils(dymu_ctx* ctx, float ms[6])
     for (int k = 0; k < 6; ++k) ms[k] = -1.0f;
     size_t n = (size_t)ctx->nx * ctx->ny, np = (size_t)ctx->pitch * ctx->rows;
     DYMU_TRY(ensure_stage(ctx));
+    ctx->terrain_staged = false;  // d_stage doubles as scratch below
     auto tick = [&](cudaEvent_t e) { return cudaEventRecord(e, ctx->stream); };
     auto lap = [&](int k) -> int {
         DYMU_CUDA_TRY(ctx, tick(ctx->ev1));

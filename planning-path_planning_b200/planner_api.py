@@ -47,6 +47,12 @@ _SIGNATURES = {
     "dymu_planner_get_reconnecting_index": (C.c_int, [C.c_void_p]),
     "dymu_planner_get_remaining_total_cost": (C.c_double, [C.c_void_p]),
     "dymu_planner_get_node_field": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "dymu_planner_cora_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]),
+    "dymu_planner_get_terrain": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "dymu_planner_fill_terrain_info": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int]),
+    "dymu_planner_update_cost": (C.c_int, [C.c_void_p, _dp, C.c_int]),
+    "dymu_planner_compute_cost_ratio": (C.c_int, [C.c_void_p, _dp, C.c_int]),
+    "dymu_planner_recompute_cost_map": (C.c_int, [C.c_void_p]),
     "dymu_planner_last_call_seconds": (C.c_double, [C.c_void_p]),
 }
 
@@ -225,6 +231,37 @@ class Planner:
     @property
     def remaining_total_cost(self):
         return float(self._l.dymu_planner_get_remaining_total_cost(self._h))
+
+    # --- CoRa: cost ratio updating after traverse (G.cpp:895-1038) ----------
+    def initCoRaMethod(self, num_terrains, num_criteria, weights):
+        w = _f64(weights)
+        return self._l.dymu_planner_cora_init(self._h, num_terrains, num_criteria, _ptr(w), w.size) == 1
+
+    def getTerrain(self, x, y):
+        return int(self._l.dymu_planner_get_terrain(self._h, x, y))
+
+    def fillTerrainInfo(self, terrain_id, data):
+        d = _f64(data)
+        return self._l.dymu_planner_fill_terrain_info(self._h, terrain_id, _ptr(d), d.size) == 1
+
+    def updateCost(self, cap=4096):
+        out = np.empty(cap, dtype=np.float64)
+        n = self._l.dymu_planner_update_cost(self._h, _ptr(out), cap)
+        if n < 0 or n > cap:
+            raise RuntimeError("update_cost failed (%d)" % n)
+        return out[:n].copy()
+
+    def computeCostRatio(self, cap=64):
+        out = np.empty(cap, dtype=np.float64)
+        n = self._l.dymu_planner_compute_cost_ratio(self._h, _ptr(out), cap)
+        if n < 0 or n > cap:
+            raise RuntimeError("compute_cost_ratio failed (%d)" % n)
+        return out[:n].copy()
+
+    def recomputeCostMap(self):
+        """computeCostMap again with the planner's current cost_lutable and the maps of the
+        previous call (kept on the host by the reference build, in HBM by the B200 build)."""
+        return self._l.dymu_planner_recompute_cost_map(self._h) == 1
 
     # --- diagnostics ------------------------------------------------------
     def node_field(self, field):

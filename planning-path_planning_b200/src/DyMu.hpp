@@ -19,7 +19,8 @@
 // globalNode / localNode are kept as plain value "views": getGlobalNode()/getLocalNode()
 // fill one from the device planes on request.  Their neighbour lists are empty (no
 // pointer graph exists any more).  The CoRa cost-ratio learning methods
-// (src/DyMu.hpp:593-608) are outside the hot-path scope of this build and report failure.
+// (src/DyMu.hpp:593-608) keep their scalar statistics on the host (DyMuCoRa.hpp); the table
+// they produce is applied on the device by recomputeCostMap().
 //
 // There is no CPU fallback: without a CUDA device initGlobalLayer returns false.
 
@@ -32,6 +33,8 @@
 #include <vector>
 
 #include <base-logging/Logging.hpp>
+
+#include "DyMuCoRa.hpp"
 
 struct dymu_ctx;
 
@@ -116,6 +119,13 @@ class DyMuPathPlanner
     std::vector<double> slope_range;
     std::vector<std::string> locomotion_modes;
     repairingAproach repairing_approach;
+
+    // CoRa state (reference: src/DyMu.hpp:429-439)
+    std::vector<segmentedTerrain> terrain_vector;
+    std::vector<double> weights;
+    int num_terrains;
+    int num_criteria;
+    double base_speed;
 
     // host-side layer bookkeeping (bit-exact emulation of hasLocalMap, DyMu.hpp:77)
     std::vector<unsigned char> has_local;
@@ -251,8 +261,7 @@ class DyMuPathPlanner
 
     int getReconnectingIndex();
 
-    // COST RATIO UPDATING AFTER TRAVERSE (CoRa) -- outside the hot-path scope: these keep
-    // the reference signatures and report failure / return the table unchanged.
+    // COST RATIO UPDATING AFTER TRAVERSE (CoRa), reference: G.cpp:895-1038
     bool initCoRaMethod(int num_terrains_, int num_criteria_, std::vector<double> weights_);
     int getTerrain(base::samples::RigidBodyState current_pos);
     bool fillTerrainInfo(int terrain_id, std::vector<double> data);
@@ -266,6 +275,13 @@ class DyMuPathPlanner
                         const std::vector<std::string>& locomotionModes, const double* elevation,
                         size_t ld_e, const double* terrainMap, size_t ld_t);
     bool getTotalCostMatrix(double* out, size_t ld);
+    // Apply the current cost_lutable (e.g. the one updateCost() just produced) to the DEM and
+    // terrain classes that are already resident in HBM -- the reference's caller would hand
+    // both maps to computeCostMap again.  With resolve=true and a goal set, the total-cost
+    // map is recomputed as well.
+    bool recomputeCostMap(bool resolve = false);
+    // read-only view of the CoRa accumulators (test tap)
+    const std::vector<segmentedTerrain>& terrainInfo() const { return terrain_vector; }
     // bulk tap of one globalNode field (DYMU_NODE_* of include/dymu_planner_c.h)
     bool getNodeFieldPlane(int field, double* out);
     // size of the dense local window in global nodes (default 64)

@@ -7,6 +7,7 @@
 // validation logic around the goal and the start node and the assembly of waypoints.
 #include "DyMu.hpp"
 
+#include <algorithm>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,6 +38,9 @@ DyMuPathPlanner::DyMuPathPlanner(double risk_distance,
       reconnect_distance(reconnect_distance),
       risk_ratio(risk_ratio),
       repairing_approach(input_approach),
+      num_terrains(0),
+      num_criteria(0),
+      base_speed(0.0),
       goal_set(false),
       goal_i(0),
       goal_j(0),
@@ -141,7 +145,14 @@ bool DyMuPathPlanner::computeCostMap(std::vector<double> cost_data,
                                      std::vector<std::vector<double>> elevation,
                                      std::vector<std::vector<double>> terrainMap)
 {
-    if (!dev) return false;
+    if (!dev)
+    {
+        // like the reference (G.cpp:151-153) the tables are recorded before anything can fail
+        this->cost_lutable = cost_data;
+        this->slope_range = slope_values;
+        this->locomotion_modes = locomotionModes;
+        return false;
+    }
     if (elevation.size() != num_nodes_Y || terrainMap.size() != num_nodes_Y) return false;
     size_t n = (size_t)num_nodes_X * num_nodes_Y;
     std::vector<double> e(n), t(n);
@@ -161,10 +172,11 @@ bool DyMuPathPlanner::computeCostMap(const std::vector<double>& cost_data,
                                      const double* elevation, size_t ld_e,
                                      const double* terrainMap, size_t ld_t)
 {
-    if (!dev) return false;
+    // recorded first, like the reference (G.cpp:151-153), also when the call then fails
     this->cost_lutable = cost_data;
     this->slope_range = slope_values;
     this->locomotion_modes = locomotionModes;
+    if (!dev) return false;
     if (cost_data.empty() || slope_values.empty() || locomotionModes.empty()) return false;
     // The reference indexes the table with terrain*range*numLocs + ... without any bound
     // check (G.cpp:237-286); refuse maps whose terrain ids do not fit the table.
@@ -634,14 +646,29 @@ bool DyMuPathPlanner::getNodeFieldPlane(int field, double* out)
     }
 }
 
-/******************************CoRa (out of scope)*****************************/
-// reference: G.cpp:895-1038 -- scalar statistics on a handful of traverse samples, not on
-// the propagation path.  The signatures are kept; the methods report failure.
-bool DyMuPathPlanner::initCoRaMethod(int, int, std::vector<double>)
+/***********************COST RATIO AFTER TRAVERSE (CoRa)************************/
+// reference: G.cpp:895-1038.  The statistics are a few scalars per terrain class and stay on
+// the host (DyMuCoRa.hpp); the table they produce feeds the device cost-map kernels again
+// through recomputeCostMap().
+bool DyMuPathPlanner::initCoRaMethod(int num_terrains_, int num_criteria_, std::vector<double> weights_)
 {
-    LOG_WARN_S << "CoRa cost-ratio learning is outside the B200 hot-path build";
-    return false;
+    num_terrains = num_terrains_;
+    num_criteria = num_criteria_;
+    if (cost_lutable.empty() || num_terrains_ < 0 || num_criteria_ < 0) return false;
+    base_speed = *std::min_element(cost_lutable.begin(), cost_lutable.end());  // G.cpp:902-904
+    if ((int)weights_.size() != num_criteria) return false;
+    weights = weights_;
+    terrain_vector.resize(num_terrains);
+    for (segmentedTerrain& t : terrain_vector)
+    {
+        t.criteria_info.resize(num_criteria);
+        t.traverse_info.resize(num_criteria);
+        t.rejected_info.resize(num_criteria);
+        t.data_samples.resize(num_criteria);
+    }
+    return true;
 }
+
 int DyMuPathPlanner::getTerrain(base::samples::RigidBodyState current_pos)
 {
     base::Pose2D pose;
@@ -650,6 +677,83 @@ int DyMuPathPlanner::getTerrain(base::samples::RigidBodyState current_pos)
     globalNode* n = getNearestGlobalNode(pose);
     return n ? (int)n->terrain - 1 : -1;
 }
-bool DyMuPathPlanner::fillTerrainInfo(int, std::vector<double>) { return false; }
-std::vector<double> DyMuPathPlanner::updateCost() { return cost_lutable; }
-std::vector<double> DyMuPathPlanner::computeCostRatio() { return std::vector<double>(); }
+// reference: G.cpp:926-938.  `data` holds one value per criterion, <= 0 meaning "no reading".
+bool DyMuPathPlanner::fillTerrainInfo(int terrain_id, std::vector<double> data)
+{
+    if (terrain_id < 0 || terrain_id >= (int)terrain_vector.size()) return false;  // reference: unchecked
+    segmentedTerrain& t = terrain_vector[terrain_id];
+    t.dataAnalysis();
+    if ((int)data.size() != num_criteria) return false;
+    for (int c = 0; c < num_criteria; ++c)
+        if (data[c] > 0) t.data_samples[c].push_back(data[c]);
+    return true;
+}
+
+// reference: G.cpp:956-993.  Chains the pairwise hardness ratios into one relative cost per
+// traversed terrain and rewrites locomotion-mode-0 rows of the table for those terrains.
+std::vector<double> DyMuPathPlanner::updateCost()
+{
+    const int range = (int)slope_range.size();
+    const int numLocs = (int)locomotion_modes.size();
+    for (int t = 0; t < num_terrains && t < (int)terrain_vector.size(); ++t) terrain_vector[t].dataAnalysis();
+
+    std::vector<double> relative(1, 1.0);
+    for (double r : computeCostRatio()) relative.push_back(relative.back() / r);
+    if (relative.size() < 2) return cost_lutable;
+    const double cheapest = *std::min_element(relative.begin(), relative.end());
+
+    size_t rank = 0;  // position of the terrain among the traversed ones
+    for (int t = 0; t < num_terrains && t < (int)terrain_vector.size(); ++t)
+    {
+        if (!terrain_vector[t].traversed) continue;
+        // The reference indexes past `relative` when a pair was skipped for lack of common
+        // criteria (G.cpp:985) and past the table for terrain ids it does not hold; both stop here.
+        if (rank >= relative.size()) break;
+        double slope_term = 0;
+        for (int s = 0; s < range; ++s)
+        {
+            slope_term += terrain_vector[t].slope_ratio * slope_range[s];  // cumulative, G.cpp:983
+            const size_t idx = (size_t)(t + 1) * range * numLocs + s;
+            if (idx < cost_lutable.size()) cost_lutable[idx] = base_speed * relative[rank] / cheapest + slope_term;
+        }
+        ++rank;
+    }
+    return cost_lutable;
+}
+
+// reference: G.cpp:999-1038.  One ratio per traversed terrain that has a traversed successor.
+std::vector<double> DyMuPathPlanner::computeCostRatio()
+{
+    std::vector<double> cost_ratios;
+    const double acc_weight = std::accumulate(weights.begin(), weights.end(), 0.0);
+    const int nt = std::min(num_terrains, (int)terrain_vector.size());
+    for (int a = 0; a + 1 < nt; ++a)
+    {
+        if (!terrain_vector[a].traversed) continue;
+        int b = a + 1;
+        while (b < nt && !terrain_vector[b].traversed) ++b;
+        if (b >= nt) continue;
+        double hardness_a = 0, hardness_b = 0;
+        for (int c = 0; c < num_criteria; ++c)
+        {
+            const costCriteria &ca = terrain_vector[a].criteria_info[c], &cb = terrain_vector[b].criteria_info[c];
+            if (ca.empty || cb.empty) continue;
+            hardness_a += weights[c] * ca.mean / acc_weight;
+            hardness_b += weights[c] * cb.mean / acc_weight;
+        }
+        if (hardness_a != 0 && hardness_b != 0) cost_ratios.push_back(hardness_a / hardness_b);
+    }
+    return cost_ratios;
+}
+
+// Extension: apply cost_lutable to the maps resident in HBM (see DyMu.hpp).
+bool DyMuPathPlanner::recomputeCostMap(bool resolve)
+{
+    if (!dev || cost_lutable.empty() || slope_range.empty() || locomotion_modes.empty()) return false;
+    if (!deviceOk(dymu_compute_cost_map(dev, cost_lutable.data(), (int)cost_lutable.size(), slope_range.data(),
+                                        (int)slope_range.size(), (int)locomotion_modes.size(), NULL, 0, NULL, 0),
+                  "recomputeCostMap"))
+        return false;
+    if (resolve && goal_set) return computeEntireTotalCostMap();
+    return true;
+}

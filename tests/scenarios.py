@@ -53,3 +53,35 @@ def repair_scenario(p, syn, path, seed=7, frame=120, res=0.1, disc_wp=12, disc_r
                 risk=p.getRiskMatrix(c[0], c[1]), deviation=p.getDeviationMatrix(c[0], c[1]),
                 hazard=p.getHazardDensityMatrix(), traff=p.getTrafficabilityMatrix(),
                 reconnecting_index=p.getReconnectingIndex())
+
+
+def cora_feed(p, n_terrains=4, n_criteria=2, weights=(1.0, 2.0), seed=5, rounds=60, tap_every=10):
+    """CoRa (G.cpp:895-1038): stream seeded traverse samples terrain by terrain and tap
+    updateCost()/computeCostRatio() along the way.  The distributions drift and jump so that the
+    accept (Student / Cochran), reject, and rejected-takes-over branches of dataAnalysis
+    (H.hpp:234-309) all run.  initCoRaMethod needs the table of a previous computeCostMap."""
+    assert p.initCoRaMethod(n_terrains, n_criteria, list(weights))
+    rng = np.random.default_rng(seed)
+    taps = []
+    for r in range(rounds):
+        for t in range(n_terrains):
+            if t == 2 and r < rounds // 2:
+                continue                      # terrain 2 is met late: ratios must skip over it
+            base = np.array([0.2 + 0.15 * t, 30.0 + 12.0 * t])
+            spread = np.array([0.02, 2.0]) * (1.0 + 0.5 * t)
+            if t == 1 and r >= rounds // 3:
+                # lasting drop (the Student test is one-sided: only lower means are rejected)
+                # -> rejected info piles up and eventually replaces the kept statistics
+                base, spread = base * 0.6, spread * 0.6
+            if t == 0 and r >= rounds // 2:
+                base = base * 1.5             # lasting rise: accepted, drags the mean along
+            if t == 3 and r % 7 == 3:
+                spread = spread * 6.0         # noisy stretch -> Cochran branch
+            for _ in range(int(rng.integers(2, 6))):
+                sample = base + spread * rng.standard_normal(n_criteria)
+                if rng.random() < 0.15:
+                    sample[int(rng.integers(0, n_criteria))] = -1.0   # "no reading"
+                assert p.fillTerrainInfo(t, sample)
+        if r % tap_every == tap_every - 1:
+            taps.append((p.computeCostRatio(), p.updateCost()))
+    return taps

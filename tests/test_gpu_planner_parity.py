@@ -151,3 +151,36 @@ def test_config2_1000_sweeping(pkg, ref_lib):
     assert ra["traj"].shape == rb["traj"].shape
     d = np.abs(ra["traj"][:, :2] - rb["traj"][:, :2]).max(axis=1)
     print("config 2 trajectory: max deviation %.3e" % d.max())
+
+
+def test_cora_loop_rebuilds_cost_map_on_device(pkg, ref_lib):
+    """traverse feedback -> updateCost (G.cpp:956-993) -> new table
+    -> cost map -> total cost.  The reference is handed both maps again; the B200 build
+    rebuilds from the elevation and terrain planes already resident in HBM.  getTerrain
+    (G.cpp:941-950) is read from the device terrain plane."""
+    nx, ny = 160, 120
+    ref, dut = _pair(pkg, ref_lib, 1, nx, ny)
+    a = sc.global_scenario(ref, pkg.synthetic, nx, ny, 4, entire=True)
+    b = sc.global_scenario(dut, pkg.synthetic, nx, ny, 4, entire=True)
+    # the transformed read-backs above reuse the staging plane the terrain map was uploaded
+    # through: the rebuild below must not depend on it
+    for x, y in ((10.2, 20.7), (80.0, 60.0), (150.4, 100.6), (0.0, 0.0)):
+        assert ref.getTerrain(x, y) == dut.getTerrain(x, y)
+    taps_a = sc.cora_feed(ref, rounds=40, tap_every=40)
+    taps_b = sc.cora_feed(dut, rounds=40, tap_every=40)
+    assert np.array_equal(taps_a[-1][1], taps_b[-1][1])
+    lut0, _, _ = pkg.synthetic.default_lut()
+    assert not np.array_equal(taps_a[-1][1], np.asarray(lut0, dtype=np.float64))
+    assert ref.recomputeCostMap() and dut.recomputeCostMap()
+    assert np.array_equal(ref.node_field(4), dut.node_field(4))            # isObstacle
+    assert rel_err(dut.node_field(2), ref.node_field(2)) <= 1e-14          # raw_cost
+    ca, cb = ref.getGlobalCostMatrix(), dut.getGlobalCostMatrix()
+    assert rel_err(cb, ca) <= 1e-14
+    assert not np.array_equal(ca, a["cost"]), "the new table did not change the cost map"
+    gx, gy = a["goal"]
+    assert ref.setGoal(gx, gy) and dut.setGoal(gx, gy)
+    assert ref.computeEntireTotalCostMap() and dut.computeEntireTotalCostMap()
+    Ta, Tb = ref.getTotalCostMatrix(), dut.getTotalCostMatrix()
+    assert np.array_equal(Ta < 0, Tb < 0)
+    assert rel_err(Tb, Ta) <= TOL_PLANE
+    assert rel_err(Tb, b["T"]) > 1e-6                                      # and it matters
