@@ -23,9 +23,31 @@
 
 int dymu_internal_fill(dymu_ctx* ctx, double* p, double v, size_t n);
 
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+
 namespace
 {
 constexpr uint32_t kNoCell = 0xFFFFFFFFu;
+
+// DYMU_TRACE_CALLS=1: wall time of every local-layer entry point on stderr (developer aid)
+struct CallTrace
+{
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit CallTrace(const char* n) : name(n), on(getenv("DYMU_TRACE_CALLS") != nullptr)
+    {
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    ~CallTrace()
+    {
+        if (on)
+            fprintf(stderr, "[dymu] %-28s %9.3f ms\n", name,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 struct LocalView
 {
@@ -193,32 +215,49 @@ __global__ void k_ingest_commit(IngestArgs a)
 // isBlockingObstacle, L.cpp:441-471: per obstacle the first in-range waypoint index feeds
 // minIndex, and the index at which the path leaves the range (or path.size()) feeds maxIndex
 // ---------------------------------------------------------------------------------
+// One warp per obstacle cell, the lanes stride over the waypoints; the sequential scan of the
+// reference becomes "first in-range index f" and "first out-of-range index after f".
 __global__ void k_blocking(LocalView v, const uint32_t* cells, uint32_t n_cells,
                            const double* path_xy, uint32_t n_path, double risk_distance,
                            uint32_t* out /* [0] min, [1] max, [2] blocked */)
 {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_cells) return;
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_cells) return;  // warp-uniform
     double wx, wy;
     world_pose(v, cells[k], wx, wy);
     bool blocked = false, left_range = false;
     uint32_t mn = 0xFFFFFFFFu, mx = 0;
-    for (uint32_t i = 0; i < n_path && !left_range; ++i)
+    for (uint32_t base = 0; base < n_path && !left_range; base += 32)
     {
-        double dx = wx - path_xy[2 * i], dy = wy - path_xy[2 * i + 1];
-        if (sqrt(dx * dx + dy * dy) < risk_distance)
+        const uint32_t i = base + lane;
+        bool in_range = false;
+        if (i < n_path)
         {
-            if (!blocked) { blocked = true; mn = i; }
-            else mx = max(mx, i);
+            double dx = wx - path_xy[2 * i], dy = wy - path_xy[2 * i + 1];
+            in_range = sqrt(dx * dx + dy * dy) < risk_distance;
         }
-        else if (blocked)
+        const unsigned valid = (n_path - base >= 32) ? full : ((1u << (n_path - base)) - 1);
+        const unsigned m = __ballot_sync(full, in_range);
+        unsigned after = valid;  // positions where leaving the range counts
+        if (!blocked)
         {
-            mx = max(mx, i);
+            if (!m) continue;
+            const uint32_t f = __ffs(m) - 1;
+            blocked = true;
+            mn = base + f;
+            after &= (f == 31) ? 0u : (full << (f + 1));
+        }
+        const unsigned leave = ~m & after;
+        if (leave)
+        {
+            mx = base + __ffs(leave) - 1;
             left_range = true;
         }
     }
     if (blocked && !left_range) mx = n_path;  // L.cpp:467-468
-    if (blocked)
+    if (blocked && lane == 0)
     {
         atomicMin(&out[0], mn);
         atomicMax(&out[1], mx);
@@ -274,11 +313,12 @@ struct MarchArgs
     int approach;            // 0 CONSERVATIVE, 1 SWEEPING
     double sx, sy, ox, oy;   // start / overtake waypoint (offset-free)
     double t_overtake, risk_ratio;
-    uint32_t* nb;            // narrow band (vector semantics: push_back / erase(begin+k))
+    uint32_t* nb;            // per window cell: narrow-band slot of the node (see k_local_march)
     uint32_t* prop;          // local_propagated_nodes
     uint32_t cap;
     uint8_t* entered;        // per window global node: the wave looked into it (L.cpp:660-662)
     int64_t* result;         // [0] end cell [1] status [2] closed [3] prop count [4] nb peak
+    const double* ltot_cache; // getTotalCost of every window cell (k_local_total_cost_cache)
     uint32_t prev_prop;      // nodes to reset from the previous call (L.cpp:589-599)
     uint64_t max_pops;
 };
@@ -301,25 +341,98 @@ __device__ __forceinline__ double local_total_cost(const LocalView& v, int64_t c
     return w00 + (w10 - w00) * a + (w01 - w00) * b + (w11 + w00 - w10 - w01) * a * b;
 }
 
-__device__ __forceinline__ double dev_or_skip(const LocalView& v, int64_t a, int64_t b)
+// The narrow band lives in shared memory as an append-only array of (cell, key) slots:
+//   * push_back  -> append at `tail`
+//   * erase(k)   -> the slot becomes a tombstone (key = +inf); relative order of the survivors,
+//                   which is what the reference's strict '<' scan breaks ties by, is untouched
+//   * a lowered deviation of a node that is already in the band rewrites its cached key through
+//     the per-cell slot map `pos`
+//   * the array is compacted (stable) when it runs full or mostly holds tombstones.
+// Keys of live slots are finite, so +inf is free to mean "erased".
+constexpr uint32_t kBandSlots = 12288;
+constexpr size_t kBandSmem = (size_t)kBandSlots * (sizeof(double) + sizeof(uint32_t));
+
+// 0: usable cell; -1: outside the global map (NULL in the reference); -2: outside the window
+__device__ __forceinline__ int cell_class(const LocalView& v, int64_t bx, int64_t by, int X, int Y)
 {
-    // propagateLocalNode's neighbour pair rule, L.cpp:705-717
-    const double* D = v.dev;
-    if (a >= 0 && b >= 0) return fmin(D[cell_addr(v, b)], D[cell_addr(v, a)]);
-    if (a < 0) return (b >= 0) ? D[cell_addr(v, b)] : DYMU_INF;
-    return D[cell_addr(v, a)];
+    int64_t LX = bx + X, LY = by + Y;
+    if (LX < 0 || LY < 0 || LX >= (int64_t)v.nx * v.r || LY >= (int64_t)v.ny * v.r) return -1;
+    if (X < 0 || Y < 0 || X >= (int)v.w || Y >= (int)v.w) return -2;
+    return 0;
+}
+
+struct MapBox
+{
+    int x0, x1, y0, y1, w;
+};
+__device__ __forceinline__ int clamp_box(int64_t t, uint32_t w)
+{
+    return (int)max((int64_t)-4, min(t, (int64_t)w + 4));
+}
+// same classes as cell_class for window coordinates within one step of the window
+__device__ __forceinline__ int box_class(const MapBox& b, int X, int Y)
+{
+    if (X < b.x0 || X >= b.x1 || Y < b.y0 || Y >= b.y1) return -1;
+    if ((unsigned)X >= (unsigned)b.w || (unsigned)Y >= (unsigned)b.w) return -2;
+    return 0;
+}
+
+// world_pose (L.cpp:35-44) from window coordinates, same expression order as global_pose()
+__device__ __forceinline__ void world_xy(const LocalView& v, uint32_t X, uint32_t Y, double& wx, double& wy)
+{
+    double px = (double)(v.gx0 + X / v.r), py = (double)(v.gy0 + Y / v.r);
+    double lx = (double)(X % v.r), ly = (double)(Y % v.r), rr = (double)v.r;
+    wx = (px - 0.5 + (0.5 / rr) + lx * (1 / rr)) / v.gres;
+    wy = (py - 0.5 + (0.5 / rr) + ly * (1 / rr)) / v.gres;
+}
+
+// propagateLocalNode's neighbour pair rule, L.cpp:705-717 (ca/cb: cell_class of the pair)
+__device__ __forceinline__ double dev_pair(const double* D, int ca, size_t oa, int cb, size_t ob)
+{
+    if (ca == 0 && cb == 0) return fmin(D[ob], D[oa]);
+    if (ca != 0) return (cb == 0) ? D[ob] : DYMU_INF;
+    return D[oa];
+}
+
+// getTotalCost(localNode*) for every window cell at once.  The march copies a value into the
+// node's total_cost the first time the wave looks at it (L.cpp:666-667), so that the lazily
+// filled plane the reference exposes stays the same while the march itself never waits for the
+// global total-cost plane.
+__global__ void k_local_total_cost_cache(LocalView v, double* cache)
+{
+    size_t total = (size_t)v.w * v.w;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride)
+    {
+        uint32_t X = (uint32_t)(c % v.w), Y = (uint32_t)(c / v.w);
+        cache[(size_t)Y * v.pitch + X] = local_total_cost(v, (int64_t)c);
+    }
 }
 
 __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
 {
+    extern __shared__ double s_key[];                      // kBandSlots keys ...
+    uint32_t* s_xy = (uint32_t*)(s_key + kBandSlots);      // ... and packed (Y << 16 | X) cells
     const LocalView& v = a.v;
     const int lane = threadIdx.x;
     const unsigned full = 0xffffffffu;
     const double inf = DYMU_INF;
+    const uint32_t w = v.w;
+    const int64_t bx = v.gx0 * (int64_t)v.r, by = v.gy0 * (int64_t)v.r;
+    // the global map in window coordinates, clamped just outside the window: all the
+    // neighbour classification below is 32-bit compares
+    const MapBox box = {clamp_box(-bx, w), clamp_box((int64_t)v.nx * v.r - bx, w),
+                        clamp_box(-by, w), clamp_box((int64_t)v.ny * v.r - by, w), (int)w};
+    // floor(X / r) == umulhi(X, r_magic) for X, r < 2^16 (r == 1 would need 2^32: handled apart)
+    const uint32_t r_magic = 0xFFFFFFFFu / v.r + 1;
+    const bool r_is_one = v.r == 1;
+    const uint32_t wg = w / v.r;
+    uint32_t* pos = a.nb;  // per window cell: slot of the node while it is in the band
     // reset of the previous propagation, L.cpp:589-599
     for (uint32_t q = lane; q < a.prev_prop; q += 32)
     {
-        size_t o = cell_addr(v, a.prop[q]);
+        uint32_t c = a.prop[q];
+        size_t o = (size_t)(c / w) * v.pitch + c % w;
         v.state[o] = 0;
         v.dev[o] = inf;
         v.ltot[o] = inf;
@@ -327,7 +440,7 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
     __syncwarp();
     int64_t status = DYMU_LOCAL_OK, end_cell = -1;
     uint64_t closed = 0;
-    uint32_t nb_n = 0, prop_n = 0, nb_peak = 0;
+    uint32_t head = 0, tail = 0, live = 0, prop_n = 0, nb_peak = 0;
     int64_t agent = cell_of(v, a.sx, a.sy);
     int64_t node_end = -1;
     double ex = 0, ey = 0;
@@ -335,17 +448,6 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
     else if (v.obst[cell_addr(v, agent)]) status = DYMU_LOCAL_START_IN_OBSTACLE;  // L.cpp:610-614
     if (status == DYMU_LOCAL_OK)
     {
-        if (lane == 0)
-        {
-            size_t o = cell_addr(v, agent);
-            v.dev[o] = 0;
-            v.ltot[o] = local_total_cost(v, agent);
-            v.state[o] = 1;
-            a.nb[0] = (uint32_t)agent;
-            a.prop[0] = (uint32_t)agent;
-        }
-        nb_n = 1;
-        prop_n = 1;
         if (a.approach == 0)
         {
             node_end = cell_of(v, a.ox, a.oy);  // L.cpp:629
@@ -353,96 +455,194 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
             else if (v.obst[cell_addr(v, node_end)]) status = DYMU_LOCAL_END_IN_OBSTACLE;
             else world_pose(v, node_end, ex, ey);
         }
-        __syncwarp();
-    }
-    uint64_t pops = 0;
-    while (status == DYMU_LOCAL_OK)
-    {
-        if (nb_n == 0) { status = DYMU_LOCAL_EXHAUSTED; break; }
-        if (++pops > a.max_pops) { status = DYMU_LOCAL_EXHAUSTED; break; }
-        // ---- minCostLocalNode: strict '<' argmin, earliest position wins (L.cpp:752-805)
-        double bk = inf;
-        uint32_t bp = 0xFFFFFFFFu;
-        for (uint32_t q = lane; q < nb_n; q += 32)
+        if (lane == 0)
         {
-            uint32_t c = a.nb[q];
-            double key = v.dev[cell_addr(v, c)];
+            size_t o = cell_addr(v, agent);
+            uint32_t AX = (uint32_t)(agent % w), AY = (uint32_t)(agent / w);
+            v.dev[o] = 0;
+            v.ltot[o] = local_total_cost(v, agent);
+            v.state[o] = 1;
+            double key = 0;
             if (a.approach == 0)
             {
                 double wx, wy;
-                world_pose(v, c, wx, wy);
+                world_xy(v, AX, AY, wx, wy);
                 key = key + sqrt((wx - ex) * (wx - ex) + (wy - ey) * (wy - ey));
             }
-            if (bp == 0xFFFFFFFFu || key < bk)
-            {
-                bk = key;
-                bp = q;
-            }
+            s_xy[0] = (AY << 16) | AX;
+            s_key[0] = key;
+            pos[agent] = 0;
+            a.prop[0] = (uint32_t)agent;
         }
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            double ok = __shfl_xor_sync(full, bk, o);
-            uint32_t op = __shfl_xor_sync(full, bp, o);
-            if (op != 0xFFFFFFFFu && (bp == 0xFFFFFFFFu || ok < bk || (ok == bk && op < bp)))
-            {
-                bk = ok;
-                bp = op;
-            }
-        }
-        const int64_t X = a.nb[bp];
+        tail = live = prop_n = 1;
         __syncwarp();
-        // ---- vector::erase(begin + bp): order-preserving shift
-        for (uint32_t base = bp; base + 1 < nb_n; base += 32)
+    }
+    uint64_t pops = 0;
+#ifdef DYMU_LOCAL_PROFILE
+    long long lm_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lm_last = clock64();
+#define LM_MARK(k)                    \
+    {                                 \
+        long long now_ = clock64();   \
+        lm_t[k] += now_ - lm_last;    \
+        lm_last = now_;               \
+    }
+#else
+#define LM_MARK(k)
+#endif
+    bool end_ready = false, end_closed = false;
+    int64_t end_addr = -1;  // lanes 0..3: the end node's neighbours, lane 4: the end node
+    while (status == DYMU_LOCAL_OK)
+    {
+        if (live == 0) { status = DYMU_LOCAL_EXHAUSTED; break; }
+        if (++pops > a.max_pops) { status = DYMU_LOCAL_EXHAUSTED; break; }
+        // ---- housekeeping: stable compaction of the slot array
+        if (tail + 4 > kBandSlots || tail - head > live + 64)
         {
-            uint32_t src = base + 1 + lane;
-            uint32_t val = (src < nb_n) ? a.nb[src] : 0;
-            __syncwarp();
-            if (src < nb_n) a.nb[src - 1] = val;
-            __syncwarp();
+            uint32_t dst = 0;
+            for (uint32_t base = head; base < tail; base += 32)
+            {
+                uint32_t q = base + lane;
+                double k = (q < tail) ? s_key[q] : inf;
+                uint32_t xy = (q < tail) ? s_xy[q] : 0;
+                bool keep = k < inf;
+                unsigned m = __ballot_sync(full, keep);
+                __syncwarp();
+                if (keep)
+                {
+                    uint32_t d = dst + __popc(m & ((1u << lane) - 1));
+                    s_key[d] = k;
+                    s_xy[d] = xy;
+                    pos[(xy >> 16) * w + (xy & 0xffffu)] = d;
+                }
+                dst += __popc(m);
+                __syncwarp();
+            }
+            head = 0;
+            tail = dst;
+            if (tail + 4 > kBandSlots) { status = DYMU_LOCAL_WINDOW_EXCEEDED; break; }
         }
-        nb_n--;
-        if (lane == 0) v.state[cell_addr(v, X)] = 1;  // CLOSED, L.cpp:653
+        LM_MARK(0);
+        // ---- minCostLocalNode: strict '<' argmin, earliest position wins (L.cpp:752-805)
+        double bk0 = inf;
+        uint32_t bp0 = 0xFFFFFFFFu;
+#pragma unroll 4
+        for (uint32_t q = head + lane; q < tail; q += 32)
+        {
+            double key = s_key[q];
+            if (key < bk0)
+            {
+                bk0 = key;
+                bp0 = q;
+            }
+        }
+        uint32_t bp;
+        {
+            // lexicographic (key, slot) minimum over the lanes; keys are non-negative (or +inf
+            // for "nothing"), so their bit patterns order like the values
+            const unsigned long long kb = (unsigned long long)__double_as_longlong(bk0);
+            const uint32_t hi = (uint32_t)(kb >> 32), lo = (uint32_t)kb;
+            const uint32_t mhi = __reduce_min_sync(full, hi);
+            const uint32_t mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xFFFFFFFFu);
+            bp = __reduce_min_sync(full, (hi == mhi && lo == mlo) ? bp0 : 0xFFFFFFFFu);
+        }
+        if (bp == 0xFFFFFFFFu) { status = DYMU_LOCAL_EXHAUSTED; break; }
+        const uint32_t pxy = s_xy[bp];
+        const int X = (int)(pxy & 0xffffu), Y = (int)(pxy >> 16);
+        const size_t oX = (size_t)Y * v.pitch + X;
+        __syncwarp();
+        // ---- vector::erase(begin + bp)
+        if (lane == 0)
+        {
+            s_key[bp] = inf;
+            v.state[oX] = 1;  // CLOSED, L.cpp:653
+        }
+        live--;
         closed++;
         __syncwarp();
-        // ---- the four neighbours on lanes 0..3 (independent: no target is another's input)
-        int64_t nbc = -1;
-        bool valid = false, is_end_candidate = false, is_new = false;
+        if (bp == head)
+        {
+            uint32_t h = head + 1;
+            while (h < tail)
+            {
+                bool lv = (h + lane < tail) && (s_key[h + lane] < inf);
+                unsigned m = __ballot_sync(full, lv);
+                if (m) { h += __ffs(m) - 1; break; }
+                h += 32;
+            }
+            head = min(h, tail);
+        }
+        LM_MARK(1);
+        // ---- the four neighbours on lanes 0..3 (independent: no target is another's input).
+        // Every value the update may need is requested up front so that a pop costs one
+        // memory round trip, not a chain of them.
+        int nX = X, nY = Y;
+        size_t o = 0;
+        uint32_t lin = 0;
+        bool is_end_candidate = false, is_new = false, lowered = false;
+        double newkey = 0;
+        if (lane < 5 && oX == (size_t)end_addr) end_closed = true;
         if (lane < 4)
         {
-            nbc = lnb4(v, X, lane);
-            if (nbc == -2) status = DYMU_LOCAL_WINDOW_EXCEEDED;
-            if (nbc >= 0)
+            if (lane == 0) nY -= 1; else if (lane == 1) nX -= 1; else if (lane == 2) nX += 1; else nY += 1;
+            int cls = box_class(box, nX, nY);
+            if (cls == -2) status = DYMU_LOCAL_WINDOW_EXCEEDED;
+            if (cls == 0)
             {
+                o = (size_t)((uint32_t)nY * v.pitch + (uint32_t)nX);
+                lin = (uint32_t)nY * w + (uint32_t)nX;
+                const int c0 = box_class(box, nX, nY - 1), c1 = box_class(box, nX - 1, nY),
+                          c2 = box_class(box, nX + 1, nY), c3 = box_class(box, nX, nY + 1);
+                const uint8_t st = v.state[o], ob = v.obst[o];
+                const double d0 = (c0 == 0) ? v.dev[o - v.pitch] : inf, d1 = (c1 == 0) ? v.dev[o - 1] : inf,
+                             d2 = (c2 == 0) ? v.dev[o + 1] : inf, d3 = (c3 == 0) ? v.dev[o + v.pitch] : inf;
+                const double R = v.risk[o], cur = v.dev[o], lt0 = v.ltot[o], ltc = a.ltot_cache[o];
+                const uint32_t slot = pos[lin];
+                LM_MARK(4);
                 // L.cpp:658-663: looking at a neighbour under a different parent subdivides it
-                int64_t gi, gj, pi, pj;
-                if (parent_via_nearest(v, nbc, gi, gj) && parent_via_nearest(v, X, pi, pj)
-                    && (gi != pi || gj != pj))
+                const uint32_t PX = r_is_one ? (uint32_t)X : __umulhi((uint32_t)X, r_magic),
+                               PY = r_is_one ? (uint32_t)Y : __umulhi((uint32_t)Y, r_magic),
+                               QX = r_is_one ? (uint32_t)nX : __umulhi((uint32_t)nX, r_magic),
+                               QY = r_is_one ? (uint32_t)nY : __umulhi((uint32_t)nY, r_magic);
+                if (QX != PX || QY != PY)
                 {
-                    int64_t ex_ = gi - v.gx0, ey_ = gj - v.gy0;
-                    uint32_t wg = v.w / v.r;
-                    if (ex_ >= 0 && ey_ >= 0 && ex_ < wg && ey_ < wg) a.entered[ey_ * wg + ex_] = 1;
+                    int64_t gi, gj, pi, pj;
+                    if (global_node_of(v, (double)(v.gx0 + QX), (double)(v.gy0 + QY), gi, gj)
+                        && global_node_of(v, (double)(v.gx0 + PX), (double)(v.gy0 + PY), pi, pj)
+                        && (gi != pi || gj != pj))
+                    {
+                        int64_t ex_ = gi - v.gx0, ey_ = gj - v.gy0;
+                        if (ex_ >= 0 && ey_ >= 0 && ex_ < wg && ey_ < wg) a.entered[ey_ * wg + ex_] = 1;
+                    }
                 }
-                size_t o = cell_addr(v, nbc);
-                valid = (v.state[o] == 0) && (!v.obst[o]);  // L.cpp:664-665
-                if (valid)
+                LM_MARK(5);
+                if ((st == 0) && (!ob))  // L.cpp:664-665
                 {
+                    LM_MARK(6);
                     // propagateLocalNode, L.cpp:700-750
-                    int64_t n0 = lnb4(v, nbc, 0), n1 = lnb4(v, nbc, 1), n2 = lnb4(v, nbc, 2),
-                            n3 = lnb4(v, nbc, 3);
-                    if (n0 == -2 || n1 == -2 || n2 == -2 || n3 == -2) status = DYMU_LOCAL_WINDOW_EXCEEDED;
+                    if (c0 == -2 || c1 == -2 || c2 == -2 || c3 == -2) status = DYMU_LOCAL_WINDOW_EXCEEDED;
                     else
                     {
-                        double Ty = dev_or_skip(v, n0, n3), Tx = dev_or_skip(v, n1, n2);
-                        double R = v.risk[o];
-                        double lt = v.ltot[o];
-                        if (lt == inf) { lt = local_total_cost(v, nbc); v.ltot[o] = lt; }
+                        // neighbour pair rule, L.cpp:705-717 (a missing neighbour reads as +inf)
+                        double Ty = (c0 == 0 && c3 == 0) ? fmin(d3, d0) : ((c0 != 0) ? d3 : d0);
+                        double Tx = (c1 == 0 && c2 == 0) ? fmin(d2, d1) : ((c1 != 0) ? d2 : d1);
+                        double lt = lt0;
+                        if (lt == inf) { lt = ltc; v.ltot[o] = lt; }
                         double C = v.lres * (a.risk_ratio * R + 1);
                         double Tn = dymu_eikonal(Tx, Ty, C);
-                        double cur = v.dev[o];
                         if (Tn < cur)
                         {
+                            LM_MARK(7);
                             is_new = (cur == inf);
+                            lowered = true;
                             v.dev[o] = Tn;
+                            newkey = Tn;
+                            if (a.approach == 0)
+                            {
+                                double wx, wy;
+                                world_xy(v, (uint32_t)nX, (uint32_t)nY, wx, wy);
+                                newkey = newkey + sqrt((wx - ex) * (wx - ex) + (wy - ey) * (wy - ey));
+                            }
+                            if (!is_new) s_key[slot] = newkey;
                         }
                         is_end_candidate = (lt < a.t_overtake) && (R == 0);  // L.cpp:668-671
                     }
@@ -450,43 +650,51 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
             }
         }
         status = __reduce_max_sync(full, (int)status);
+        LM_MARK(2);
         if (status != DYMU_LOCAL_OK) break;
         // push_back in nb4 order, L.cpp:742-747
         unsigned newmask = __ballot_sync(full, is_new);
+        uint32_t added = __popc(newmask);
+        if (prop_n + added >= a.cap) { status = DYMU_LOCAL_WINDOW_EXCEEDED; break; }
         if (is_new)
         {
             uint32_t off = __popc(newmask & ((1u << lane) - 1));
-            if (nb_n + off < a.cap && prop_n + off < a.cap)
-            {
-                a.nb[nb_n + off] = (uint32_t)nbc;
-                a.prop[prop_n + off] = (uint32_t)nbc;
-            }
+            s_xy[tail + off] = ((uint32_t)nY << 16) | (uint32_t)nX;
+            s_key[tail + off] = newkey;
+            pos[lin] = tail + off;
+            a.prop[prop_n + off] = lin;
         }
-        uint32_t added = __popc(newmask);
-        if (nb_n + added >= a.cap || prop_n + added >= a.cap) { status = DYMU_LOCAL_WINDOW_EXCEEDED; break; }
-        nb_n += added;
+        tail += added;
+        live += added;
         prop_n += added;
-        nb_peak = max(nb_peak, nb_n);
+        nb_peak = max(nb_peak, live);
         if (node_end < 0)
         {
             unsigned cm = __ballot_sync(full, is_end_candidate);
             if (cm)
             {
                 int src = __ffs(cm) - 1;
-                node_end = __shfl_sync(full, nbc, src);
+                node_end = (int64_t)__shfl_sync(full, lin, src);
             }
         }
         __syncwarp();
-        // ---- end test, L.cpp:674-684
+        LM_MARK(3);
+        // ---- end test, L.cpp:674-684: the end node and its four neighbours are CLOSED.
+        // Their state is read once when the end node becomes known and then followed in
+        // registers (a node is CLOSED exactly when it is popped).
         if (node_end >= 0)
         {
-            bool ok = true;
-            if (lane < 5)
+            if (!end_ready)
             {
-                int64_t c = (lane == 4) ? node_end : lnb4(v, node_end, lane);
-                ok = (c >= 0) && (v.state[cell_addr(v, c)] == 1);
+                if (lane < 5)
+                {
+                    int64_t c = (lane == 4) ? node_end : lnb4(v, node_end, lane);
+                    end_addr = (c >= 0) ? (int64_t)cell_addr(v, c) : -1;
+                    end_closed = (end_addr >= 0) && (v.state[end_addr] == 1);
+                }
+                end_ready = true;
             }
-            if (__all_sync(full, ok))
+            if (__all_sync(full, lane >= 5 || end_closed))
             {
                 end_cell = node_end;
                 break;
@@ -500,6 +708,10 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
         a.result[2] = (int64_t)closed;
         a.result[3] = prop_n;
         a.result[4] = nb_peak;
+#ifdef DYMU_LOCAL_PROFILE
+        // cycles: [5] end test + housekeeping, [6] argmin + erase, [7] neighbours, [8] push
+        for (int k = 0; k < 8; ++k) a.result[5 + k] = lm_t[k];
+#endif
     }
 }
 
@@ -752,6 +964,7 @@ extern "C" {
 
 int dymu_local_create(dymu_ctx* ctx, uint32_t wg)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || wg < 3) return DYMU_ERR_ARG;
     dymu_internal_local_free(ctx);
     dymu_local& l = ctx->loc;
@@ -782,6 +995,7 @@ int dymu_local_create(dymu_ctx* ctx, uint32_t wg)
 
 int dymu_local_anchor(dymu_ctx* ctx, int64_t gx0, int64_t gy0)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated) return DYMU_ERR_STATE;
     ctx->loc.gx0 = gx0;
     ctx->loc.gy0 = gy0;
@@ -790,6 +1004,7 @@ int dymu_local_anchor(dymu_ctx* ctx, int64_t gx0, int64_t gy0)
 
 int dymu_local_info(const dymu_ctx* ctx, int64_t* gx0, int64_t* gy0, uint32_t* wg, uint32_t* r)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated) return DYMU_ERR_STATE;
     if (gx0) *gx0 = ctx->loc.gx0;
     if (gy0) *gy0 = ctx->loc.gy0;
@@ -812,6 +1027,7 @@ static double* lplane(dymu_ctx* ctx, int p)
 int dymu_local_read_rect(dymu_ctx* ctx, int lplane_id, uint32_t x0, uint32_t y0, uint32_t w,
                          uint32_t h, double* host)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !host) return DYMU_ERR_ARG;
     const dymu_local& l = ctx->loc;
     double* d = lplane(ctx, lplane_id);
@@ -826,6 +1042,7 @@ int dymu_local_read_rect(dymu_ctx* ctx, int lplane_id, uint32_t x0, uint32_t y0,
 int dymu_local_read_rect_u8(dymu_ctx* ctx, int lplane_id, uint32_t x0, uint32_t y0, uint32_t w,
                             uint32_t h, uint8_t* host)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !host) return DYMU_ERR_ARG;
     const dymu_local& l = ctx->loc;
     uint8_t* d = lplane_id == DYMU_LPLANE_U8_OBSTACLE ? l.obst
@@ -841,6 +1058,7 @@ int dymu_local_ingest(dymu_ctx* ctx, const uint8_t* image, uint32_t w, uint32_t 
                       uint32_t row_size, uint32_t pixel_size, double res, double rover_x,
                       double rover_y, uint32_t* new_cells, uint32_t cap, uint32_t* n_new)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !image || !new_cells || !n_new || w == 0 || h == 0
         || row_size < w * pixel_size || pixel_size == 0)
         return DYMU_ERR_ARG;
@@ -892,6 +1110,7 @@ int dymu_local_blocking(dymu_ctx* ctx, const uint32_t* cells, uint32_t n_cells,
                         const double* path_xy, uint32_t n_path, double risk_distance,
                         uint32_t* min_index, uint32_t* max_index, int* blocked)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !min_index || !max_index || !blocked) return DYMU_ERR_ARG;
     *blocked = 0;
     if (n_cells == 0 || n_path == 0) return DYMU_OK;
@@ -905,7 +1124,7 @@ int dymu_local_blocking(dymu_ctx* ctx, const uint32_t* cells, uint32_t n_cells,
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, hp, 16 + (size_t)n_path * 16 + (size_t)n_cells * 4,
                                        cudaMemcpyHostToDevice, ctx->stream));
     char* dp = (char*)ctx->d_scratch;
-    k_blocking<<<dymu_div_up(n_cells, 64), 64, 0, ctx->stream>>>(
+    k_blocking<<<dymu_div_up(n_cells, 4), 128, 0, ctx->stream>>>(
         make_view(ctx), (const uint32_t*)(dp + 16 + (size_t)n_path * 16), n_cells,
         (const double*)(dp + 16), n_path, risk_distance, (uint32_t*)dp);
     ctx->launches++;
@@ -920,6 +1139,7 @@ int dymu_local_blocking(dymu_ctx* ctx, const uint32_t* cells, uint32_t n_cells,
 
 int dymu_local_expand_risk(dymu_ctx* ctx, double risk_distance, dymu_solve_stats* stats)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !(risk_distance > 0)) return DYMU_ERR_ARG;
     dymu_local& l = ctx->loc;
     size_t n = (size_t)l.pitch * l.rows;
@@ -948,6 +1168,7 @@ int dymu_local_propagate(dymu_ctx* ctx, int approach, double start_x, double sta
                          double risk_ratio, int64_t* end_cell, uint32_t* status,
                          uint64_t* n_closed)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !end_cell || !status) return DYMU_ERR_ARG;
     dymu_local& l = ctx->loc;
     dymu_local* e = extra_of(ctx);
@@ -961,13 +1182,35 @@ int dymu_local_propagate(dymu_ctx* ctx, int approach, double start_x, double sta
     a.result = (int64_t*)ctx->d_scratch;
     a.prev_prop = e->prop_count;
     a.max_pops = (uint64_t)l.w * l.w;
-    k_local_march<<<1, 32, 0, ctx->stream>>>(a);
+    // crisk is scratch between two risk dilations (dymu_local_expand_risk rebuilds it)
+    a.ltot_cache = l.crisk;
+    {
+        size_t cells = (size_t)l.w * l.w;
+        uint32_t grid = (uint32_t)std::min<size_t>((cells + 255) / 256, (size_t)ctx->sm_count * 8);
+        k_local_total_cost_cache<<<grid, 256, 0, ctx->stream>>>(a.v, l.crisk);
+        ctx->launches++;
+        DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(k_local_march, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)kBandSmem));
+    k_local_march<<<1, 32, kBandSmem, ctx->stream>>>(a);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     int64_t* h = (int64_t*)ctx->h_pinned;
-    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, a.result, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, a.result, 13 * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                        ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (getenv("DYMU_TRACE_CALLS"))
+    {
+        fprintf(stderr, "[dymu]   march: status %lld, %lld nodes closed, %lld propagated, band peak %lld\n",
+                (long long)h[1], (long long)h[2], (long long)h[3], (long long)h[4]);
+#ifdef DYMU_LOCAL_PROFILE
+        fprintf(stderr, "[dymu]   cycles: end/housekeeping %lld, argmin %lld, neighbours %lld, push %lld\n",
+                (long long)h[5], (long long)h[6], (long long)h[7], (long long)h[8]);
+        fprintf(stderr, "[dymu]   lane 0 inside neighbours: to loads issued %lld, parent check %lld, state wait %lld, update %lld\n",
+                (long long)h[9], (long long)h[10], (long long)h[11], (long long)h[12]);
+#endif
+    }
     *end_cell = h[0];
     *status = (uint32_t)h[1];
     if (n_closed) *n_closed = (uint64_t)h[2];
@@ -979,6 +1222,7 @@ int dymu_local_extract_path(dymu_ctx* ctx, int64_t end_cell, double start_x, dou
                             double offset_x, double offset_y, double* out, uint32_t cap,
                             uint32_t* n_out, int* status)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !out || !n_out || !status || cap == 0) return DYMU_ERR_ARG;
     const dymu_local& l = ctx->loc;
     if (end_cell < 0 || end_cell >= (int64_t)l.w * l.w) return DYMU_ERR_ARG;
@@ -1011,6 +1255,7 @@ int dymu_local_extract_path(dymu_ctx* ctx, int64_t end_cell, double start_x, dou
 
 int dymu_local_sample_risk(dymu_ctx* ctx, const double* xy, uint32_t n, double* risk_out)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !xy || !risk_out) return DYMU_ERR_ARG;
     if (n == 0) return DYMU_OK;
     size_t need = (size_t)n * 24;
@@ -1031,6 +1276,7 @@ int dymu_local_sample_risk(dymu_ctx* ctx, const double* xy, uint32_t n, double* 
 
 int dymu_local_read_entered(dymu_ctx* ctx, uint8_t* host, int clear)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !host) return DYMU_ERR_ARG;
     dymu_local& l = ctx->loc;
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(host, l.entered, (size_t)l.wg * l.wg, cudaMemcpyDeviceToHost,
@@ -1042,6 +1288,7 @@ int dymu_local_read_entered(dymu_ctx* ctx, uint8_t* host, int clear)
 
 int dymu_local_cell_of(dymu_ctx* ctx, double x, double y, int64_t* cell)
 {
+    CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !cell) return DYMU_ERR_ARG;
     k_cell_of<<<1, 1, 0, ctx->stream>>>(make_view(ctx), x, y, (int64_t*)ctx->d_scratch);
     ctx->launches++;
