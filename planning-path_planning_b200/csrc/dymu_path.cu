@@ -3,25 +3,29 @@
 // interpolate, src/DyMu_GlobalPathPlanning.cpp:615-784).
 //
 // The descent is a sequential chain (each waypoint depends on the previous one), so it is
-// latency-bound, not bandwidth-bound: one warp walks one path.  The warp keeps a
-// PATCH x PATCH window of T and of the elevation in shared memory and re-centres it only
-// when the 4x4 stencil of the current cell leaves it (a 0.4-cell step stays inside for
-// ~100 steps), so the per-step loads are shared-memory hits.  Lanes 0..3 evaluate the four
-// cell-corner gradients in parallel, the results are exchanged with warp shuffles and every
-// lane carries the identical waypoint state, so there is no divergence; lane 0 stores the
-// waypoint.  Batches of queries run one warp (one CTA) per query.
+// latency-bound, not bandwidth-bound: one warp walks one path.  The CTA keeps a
+// PATCH x PATCH window in shared memory: total cost, elevation and -- computed by all eight
+// warps right after a (re)load -- the normalised node gradients of gradientNode.  A step of
+// the walker is then twelve shared-memory reads and three bilinear interpolations; the
+// square root and the two divisions per corner are off the per-step chain.  The window is
+// re-placed only when the 4x4 stencil of the current cell leaves it, shifted ahead in the
+// direction of travel.  Every lane of the walker carries the identical waypoint state (no
+// divergence); lane 0 stores the waypoint.  Batches of queries run one CTA per query.
 #include <limits.h>
 
 #include "dymu_ctx.cuh"
 
 namespace
 {
-constexpr int PATCH = 64;  // cells per patch edge: 2 x 32 KB of shared memory
+constexpr int PATCH = 64;  // cells per patch edge: 4 x 32 KB of shared memory
+constexpr int PATCH_LEAD = 20;  // how far the window is shifted ahead of the walker
 
 struct Patch
 {
     double* t;   // PATCH x PATCH total cost
     double* e;   // PATCH x PATCH elevation
+    double* gx;  // PATCH x PATCH normalised gradient (valid one cell inside the border)
+    double* gy;
     int x0, y0;  // grid coordinates of patch cell (0,0); valid region clipped to the grid
     bool valid;
 };
@@ -106,14 +110,35 @@ __device__ __forceinline__ void load_patch(const PathArgs& a, double* pt_t, doub
     }
 }
 
-// makes sure cells [cx-1, cx+2] x [cy-1, cy+2] are inside the shared-memory window
+// second half of a reload (after a barrier): gradientNode for every node whose stencil is
+// inside the window
+__device__ __forceinline__ void patch_gradients(const PathArgs& a, const Patch& pt)
+{
+    for (int k = threadIdx.x; k < PATCH * PATCH; k += PATH_THREADS)
+    {
+        int r = k / PATCH, c = k % PATCH;
+        int gx = pt.x0 + c, gy = pt.y0 + r;
+        double dnx = 0, dny = 0;
+        if (r >= 1 && c >= 1 && r < PATCH - 1 && c < PATCH - 1 && gx >= 0 && gy >= 0 && gx < (int)a.nx
+            && gy < (int)a.ny)
+            grad_node(a, pt, (uint32_t)gx, (uint32_t)gy, dnx, dny);
+        pt.gx[k] = dnx;
+        pt.gy[k] = dny;
+    }
+}
+
+// makes sure cells [cx-1, cx+2] x [cy-1, cy+2] are inside the shared-memory window; a new
+// window is placed PATCH_LEAD cells ahead along the last step (dirx, diry in [-1, 1])
 __device__ __forceinline__ void ensure_patch(const PathArgs& a, Patch& pt, PatchCmd* cmd, int lane, int cx,
-                                             int cy)
+                                             int cy, double dirx, double diry)
 {
     if (pt.valid && cx - 1 >= pt.x0 && cy - 1 >= pt.y0 && cx + 2 < pt.x0 + PATCH && cy + 2 < pt.y0 + PATCH)
         return;
-    pt.x0 = cx - PATCH / 2;
-    pt.y0 = cy - PATCH / 2;
+    int lx = (dirx == dirx) ? (int)(dirx * PATCH_LEAD) : 0, ly = (diry == diry) ? (int)(diry * PATCH_LEAD) : 0;
+    lx = max(-PATCH_LEAD, min(PATCH_LEAD, lx));
+    ly = max(-PATCH_LEAD, min(PATCH_LEAD, ly));
+    pt.x0 = cx - PATCH / 2 + lx;
+    pt.y0 = cy - PATCH / 2 + ly;
     pt.valid = true;
     if (lane == 0)
     {
@@ -123,33 +148,29 @@ __device__ __forceinline__ void ensure_patch(const PathArgs& a, Patch& pt, Patch
     __syncthreads();  // helpers are parked at the matching barrier
     load_patch(a, pt.t, pt.e, pt.x0, pt.y0);
     __syncthreads();
+    patch_gradients(a, pt);
+    __syncthreads();
 }
 
+template <bool UNIT_RES>
 __device__ __forceinline__ bool next_waypoint(const PathArgs& a, Patch& pt, PatchCmd* cmd, int lane,
                                               double wx, double wy, double& z, double& dCx,
                                               double& dCy, double& nx_, double& ny_)
 {
-    // x / 1.0 == x exactly: skip the two fp64 divisions for the usual global_res = 1
-    const bool unit = (a.gres == 1.0);
-    double gx = unit ? wx : wx / a.gres, gy = unit ? wy : wy / a.gres;
+    // x / 1.0 == x exactly: the usual global_res = 1 gets its own instantiation without the
+    // two fp64 divisions (as a run-time select the compiler still evaluated them every step)
+    double gx = UNIT_RES ? wx : wx / a.gres, gy = UNIT_RES ? wy : wy / a.gres;
     if (!(gx >= 0.0) || !(gy >= 0.0) || !(gx < (double)(a.nx - 1)) || !(gy < (double)(a.ny - 1)))
         return false;
     uint32_t cx = (uint32_t)gx, cy = (uint32_t)gy;
     double da = gx - (double)cx, db = gy - (double)cy;
-    ensure_patch(a, pt, cmd, lane, (int)cx, (int)cy);
-    // lane c (0..3) owns corner (cx + (c&1), cy + (c>>1)): 0=n00 1=n10 2=n01 3=n11
-    int c = lane & 3;
-    uint32_t ci = cx + (uint32_t)(c & 1), cj = cy + (uint32_t)(c >> 1);
-    double gxc, gyc;
-    grad_node(a, pt, ci, cj, gxc, gyc);
-    double ec = pt.e[((int)cj - pt.y0) * PATCH + ((int)ci - pt.x0)];
-    const unsigned full = 0xffffffffu;
-    double gx00 = __shfl_sync(full, gxc, 0), gx10 = __shfl_sync(full, gxc, 1);
-    double gx01 = __shfl_sync(full, gxc, 2), gx11 = __shfl_sync(full, gxc, 3);
-    double gy00 = __shfl_sync(full, gyc, 0), gy10 = __shfl_sync(full, gyc, 1);
-    double gy01 = __shfl_sync(full, gyc, 2), gy11 = __shfl_sync(full, gyc, 3);
-    double e00 = __shfl_sync(full, ec, 0), e10 = __shfl_sync(full, ec, 1);
-    double e01 = __shfl_sync(full, ec, 2), e11 = __shfl_sync(full, ec, 3);
+    ensure_patch(a, pt, cmd, lane, (int)cx, (int)cy, -dCx, -dCy);  // dCx/dCy: previous step
+    // corners n00 = (cx, cy), n10 = (cx+1, cy), n01 = (cx, cy+1), n11 = (cx+1, cy+1)
+    const int k00 = ((int)cy - pt.y0) * PATCH + ((int)cx - pt.x0);
+    const int k10 = k00 + 1, k01 = k00 + PATCH, k11 = k00 + PATCH + 1;
+    const double gx00 = pt.gx[k00], gx10 = pt.gx[k10], gx01 = pt.gx[k01], gx11 = pt.gx[k11];
+    const double gy00 = pt.gy[k00], gy10 = pt.gy[k10], gy01 = pt.gy[k01], gy11 = pt.gy[k11];
+    const double e00 = pt.e[k00], e10 = pt.e[k10], e01 = pt.e[k01], e11 = pt.e[k11];
     dCx = dymu_interp(da, db, gx00, gx01, gx10, gx11);
     dCy = dymu_interp(da, db, gy00, gy01, gy10, gy11);
     // elevation corners are passed as (e00, e10, e01, e11) into (g00, g01, g10, g11):
@@ -160,12 +181,36 @@ __device__ __forceinline__ bool next_waypoint(const PathArgs& a, Patch& pt, Patc
     return true;
 }
 
-__device__ __forceinline__ double dist2d(double ax, double ay, double bx, double by)
+// The reference compares sqrt(d2) with a constant twice per step (G.cpp:633, 649).  sqrt is
+// correctly rounded and monotone, so "sqrt(d2) > c" is "d2 > hi(c)" with hi(c) the largest
+// double whose root does not exceed c, and "sqrt(d2) < c" is "d2 < lo(c)" with lo(c) the
+// smallest double whose root reaches c.  Both thresholds are found once per path; the
+// per-step tests are then exact without a square root on the dependency chain.
+__device__ __forceinline__ double dist2(double ax, double ay, double bx, double by)
 {
-    return sqrt((ax - bx) * (ax - bx) + (ay - by) * (ay - by));
+    return (ax - bx) * (ax - bx) + (ay - by) * (ay - by);
+}
+__device__ __forceinline__ double next_up(double x) { return __longlong_as_double(__double_as_longlong(x) + 1); }
+__device__ __forceinline__ double next_down(double x) { return __longlong_as_double(__double_as_longlong(x) - 1); }
+__device__ double sqrt_gt_threshold(double c)
+{
+    if (!(c > 0)) return (c == 0) ? 0.0 : -1.0;  // sqrt(x) > 0 <=> x > 0; any x >= 0 beats a negative c
+    double t = c * c;
+    while (sqrt(t) > c) t = next_down(t);
+    while (sqrt(next_up(t)) <= c) t = next_up(t);
+    return t;  // sqrt(x) > c  <=>  x > t
+}
+__device__ double sqrt_lt_threshold(double c)
+{
+    if (!(c > 0)) return 0.0;  // sqrt(x) < c never holds
+    double t = c * c;
+    while (sqrt(t) < c) t = next_up(t);
+    while (t > 0 && sqrt(next_down(t)) >= c) t = next_down(t);
+    return t;  // sqrt(x) < c  <=>  x < t
 }
 
 // computeGlobalPath, G.cpp:615-662
+template <bool UNIT_RES>
 __global__ void __launch_bounds__(PATH_THREADS, 1) k_global_path(const PathArgs* args_arr)
 {
     const PathArgs a = args_arr[blockIdx.x];
@@ -175,6 +220,8 @@ __global__ void __launch_bounds__(PATH_THREADS, 1) k_global_path(const PathArgs*
     Patch pt;
     pt.t = path_smem;
     pt.e = path_smem + PATCH * PATCH;
+    pt.gx = path_smem + 2 * PATCH * PATCH;
+    pt.gy = path_smem + 3 * PATCH * PATCH;
     pt.x0 = pt.y0 = 0;
     pt.valid = false;
     if (threadIdx.x >= 32)
@@ -185,13 +232,17 @@ __global__ void __launch_bounds__(PATH_THREADS, 1) k_global_path(const PathArgs*
             __syncthreads();
             const int x0 = cmd.x0, y0 = cmd.y0;
             if (x0 == INT_MIN) return;
+            pt.x0 = x0;
+            pt.y0 = y0;
             load_patch(a, pt.t, pt.e, x0, y0);
+            __syncthreads();
+            patch_gradients(a, pt);
             __syncthreads();
         }
     }
     const double sx = a.gres * (double)a.goal_i, sy = a.gres * (double)a.goal_j;
     uint32_t n = 0, status = DYMU_PATH_OK;
-    double wx = a.x0, wy = a.y0, z, dCx, dCy, nx_, ny_;
+    double wx = a.x0, wy = a.y0, z, dCx = 0, dCy = 0, nx_, ny_;
 
     auto push = [&](double x, double y, double zz, double dx, double dy) -> bool {
         if (n >= a.cap) return false;
@@ -204,16 +255,18 @@ __global__ void __launch_bounds__(PATH_THREADS, 1) k_global_path(const PathArgs*
         return true;
     };
 
-    if (!next_waypoint(a, pt, &cmd, lane, wx, wy, z, dCx, dCy, nx_, ny_)) status = DYMU_PATH_OUTSIDE;
+    if (!next_waypoint<UNIT_RES>(a, pt, &cmd, lane, wx, wy, z, dCx, dCy, nx_, ny_)) status = DYMU_PATH_OUTSIDE;
     else if (isnan(nx_) || isnan(ny_)) status = DYMU_PATH_NAN;
     else
     {
         push(wx, wy, z, dCx, dCy);
         wx = nx_;
         wy = ny_;
-        while (dist2d(wx, wy, sx, sy) > 2.0 * a.gres)
+        const double far2 = sqrt_gt_threshold(2.0 * a.gres);            // dist > 2 * global_res
+        const double stall2 = sqrt_lt_threshold(0.01 * a.tau * a.gres);  // dist < 0.01 * tau * global_res
+        while (dist2(wx, wy, sx, sy) > far2)
         {
-            if (!next_waypoint(a, pt, &cmd, lane, wx, wy, z, dCx, dCy, nx_, ny_))
+            if (!next_waypoint<UNIT_RES>(a, pt, &cmd, lane, wx, wy, z, dCx, dCy, nx_, ny_))
             {
                 status = DYMU_PATH_OUTSIDE;
                 break;
@@ -223,7 +276,7 @@ __global__ void __launch_bounds__(PATH_THREADS, 1) k_global_path(const PathArgs*
                 status = DYMU_PATH_CAPACITY;
                 break;
             }
-            if (dist2d(wx, wy, nx_, ny_) < 0.01 * a.tau * a.gres)
+            if (dist2(wx, wy, nx_, ny_) < stall2)
             {
                 status = DYMU_PATH_STALLED;
                 break;
@@ -241,6 +294,14 @@ __global__ void __launch_bounds__(PATH_THREADS, 1) k_global_path(const PathArgs*
         cmd.x0 = INT_MIN;  // release the helper warps
     }
     __syncthreads();
+}
+
+int launch_paths(dymu_ctx* ctx, uint32_t n, size_t smem, const PathArgs* d_args)
+{
+    auto kernel = (ctx->gres == 1.0) ? k_global_path<true> : k_global_path<false>;
+    DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<n, PATH_THREADS, smem, ctx->stream>>>(d_args);
+    return DYMU_OK;
 }
 }  // namespace
 
@@ -269,10 +330,8 @@ int dymu_extract_global_path(dymu_ctx* ctx, uint32_t slot, double x0, double y0,
     *h_args = a;
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, h_args, sizeof(PathArgs),
                                        cudaMemcpyHostToDevice, ctx->stream));
-    const size_t smem = 2 * PATCH * PATCH * sizeof(double);
-    DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(k_global_path, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-    k_global_path<<<1, PATH_THREADS, smem, ctx->stream>>>((const PathArgs*)ctx->d_scratch);
+    const size_t smem = 4 * PATCH * PATCH * sizeof(double);
+    DYMU_TRY(launch_paths(ctx, 1, smem, (const PathArgs*)ctx->d_scratch));
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     uint32_t* h_res = (uint32_t*)((char*)ctx->h_pinned + sizeof(PathArgs));
@@ -319,10 +378,8 @@ int dymu_extract_global_path_batch(dymu_ctx* ctx, uint32_t n, const uint32_t* sl
     }
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(d_base, h_args, (size_t)n * sizeof(PathArgs), cudaMemcpyHostToDevice,
                                        ctx->stream));
-    const size_t smem = 2 * PATCH * PATCH * sizeof(double);
-    DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(k_global_path, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-    k_global_path<<<n, PATH_THREADS, smem, ctx->stream>>>((const PathArgs*)d_base);
+    const size_t smem = 4 * PATCH * PATCH * sizeof(double);
+    DYMU_TRY(launch_paths(ctx, n, smem, (const PathArgs*)d_base));
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     uint32_t* h_res = (uint32_t*)((char*)ctx->h_pinned + (size_t)n * sizeof(PathArgs));
