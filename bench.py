@@ -346,8 +346,10 @@ def run_b200(args):
     def plan_e2e():
         dev.set_cost_map(cost_host.numpy())
         dev.solve_total_cost([goal])
+        # getTotalCostMatrix read-back runs on the copy stream while the path is extracted
+        dev.download_total_cost_begin(t_host.numpy(), xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
         dev.extract_global_path(float(start[0]), float(start[1]), 0.4, goal[0], goal[1])
-        dev.download_total_cost(xform=pkg.cuda_api.XFORM_INF_TO_MINUS1, out=t_host.numpy())
+        dev.download_total_cost_end()
 
     for _ in range(min(2, args.warmup)):
         plan_e2e()

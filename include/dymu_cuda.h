@@ -164,6 +164,13 @@ int dymu_count_reached(dymu_ctx* ctx, uint32_t slot, uint64_t* n_finite);
 int dymu_stop_threshold(dymu_ctx* ctx, uint32_t slot, uint32_t start_i, uint32_t start_j,
                         double* t_stop);
 int dymu_download_total_cost(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform);
+/* getTotalCostMatrix (G.cpp:799-811) overlapped with getPath (G.cpp:589-611): _begin forks a
+ * copy stream behind everything queued so far and returns at once; the caller may run
+ * dymu_extract_global_path meanwhile, but nothing that changes the total-cost plane or
+ * downloads another transformed plane; _end waits for the copy.  `host` should be pinned
+ * memory, otherwise the copy is not asynchronous. */
+int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform);
+int dymu_download_total_cost_end(dymu_ctx* ctx);
 /* values of a plane at n cells (k = j*nx+i), for getTotalCost(Waypoint) G.cpp:860-890 */
 int dymu_read_cells(dymu_ctx* ctx, int plane, uint32_t slot, const uint32_t* cell_index,
                     uint32_t n, double* out);

@@ -393,6 +393,8 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
     ctx->n_slots = 1;
     *out = ctx;  // from here on the caller owns ctx and can read the error text
     DYMU_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    DYMU_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev2));
@@ -438,6 +440,8 @@ int dymu_destroy(dymu_ctx* ctx)
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     for (int k = 0; k < 8; ++k)
         if (ctx->user_ev[k]) cudaEventDestroy(ctx->user_ev[k]);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
     return DYMU_OK;
@@ -509,27 +513,34 @@ static int ensure_stage(dymu_ctx* ctx)
     return DYMU_OK;
 }
 
-static int download_f64(dymu_ctx* ctx, const double* d, double* host, size_t ld, int xform)
+static int download_f64_on(dymu_ctx* ctx, cudaStream_t st, const double* d, double* host, size_t ld,
+                           int xform)
 {
     if (xform == DYMU_XFORM_NONE)
     {
         DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(host, ld * sizeof(double), d,
                                              ctx->pitch * sizeof(double), ctx->nx * sizeof(double),
-                                             ctx->ny, cudaMemcpyDeviceToHost, ctx->stream));
+                                             ctx->ny, cudaMemcpyDeviceToHost, st));
     }
     else
     {
         DYMU_TRY(ensure_stage(ctx));
         ctx->terrain_staged = false;  // the staging plane is about to be overwritten
         size_t n = (size_t)ctx->nx * ctx->ny;
-        k_readback<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(
+        k_readback<<<stream_grid(ctx, n), kThreads, 0, st>>>(
             d, ctx->haz, ctx->traff, ctx->obst, ctx->d_stage, xform, ctx->pitch, ctx->nx, ctx->ny);
         ctx->launches++;
         DYMU_CUDA_TRY(ctx, cudaGetLastError());
         DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(host, ld * sizeof(double), ctx->d_stage,
                                              ctx->nx * sizeof(double), ctx->nx * sizeof(double),
-                                             ctx->ny, cudaMemcpyDeviceToHost, ctx->stream));
+                                             ctx->ny, cudaMemcpyDeviceToHost, st));
     }
+    return DYMU_OK;
+}
+
+static int download_f64(dymu_ctx* ctx, const double* d, double* host, size_t ld, int xform)
+{
+    DYMU_TRY(download_f64_on(ctx, ctx->stream, d, host, ld, xform));
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return DYMU_OK;
 }
@@ -547,6 +558,26 @@ int dymu_download_total_cost(dymu_ctx* ctx, uint32_t slot, double* host, size_t 
 {
     if (!ctx || !host || ld < ctx->nx || slot >= ctx->n_slots) return DYMU_ERR_ARG;
     return download_f64(ctx, ctx->T + (size_t)slot * ctx->pitch * ctx->rows, host, ld, xform);
+}
+
+int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform)
+{
+    if (!ctx || !host || ld < ctx->nx || slot >= ctx->n_slots) return DYMU_ERR_ARG;
+    if (xform != DYMU_XFORM_NONE) DYMU_TRY(ensure_stage(ctx));  // allocate before forking
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    return download_f64_on(ctx, ctx->copy_stream, ctx->T + (size_t)slot * ctx->pitch * ctx->rows, host, ld,
+                           xform);
+}
+
+int dymu_download_total_cost_end(dymu_ctx* ctx)
+{
+    if (!ctx) return DYMU_ERR_ARG;
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    // later work on the main stream may overwrite the plane or the staging buffer
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    return DYMU_OK;
 }
 
 int dymu_download_plane_u8(dymu_ctx* ctx, int plane, uint8_t* host, size_t ld)

@@ -72,6 +72,8 @@ _SIG = {
     "dymu_count_reached": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
     "dymu_stop_threshold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp]),
     "dymu_download_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_size_t, C.c_int]),
+    "dymu_download_total_cost_begin": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_size_t, C.c_int]),
+    "dymu_download_total_cost_end": (C.c_int, [C.c_void_p]),
     "dymu_read_cells": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, _u32p, C.c_uint32, _dp]),
     "dymu_read_node": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _dp]),
     "dymu_count_leq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.POINTER(C.c_uint64)]),
@@ -313,6 +315,15 @@ class DeviceLayer:
         self._chk(self._l.dymu_download_total_cost(self._h, slot, out.ctypes.data_as(_dp),
                                                    out.shape[1], xform))
         return out
+
+    def download_total_cost_begin(self, out, slot=0, xform=XFORM_NONE):
+        """Start the read-back on the copy stream; `out` (pinned for a truly asynchronous copy)
+        is valid after download_total_cost_end()."""
+        self._chk(self._l.dymu_download_total_cost_begin(self._h, slot, out.ctypes.data_as(_dp),
+                                                         out.shape[1], xform))
+
+    def download_total_cost_end(self):
+        self._chk(self._l.dymu_download_total_cost_end(self._h))
 
     def read_cells(self, name, cells, slot=0):
         idx = np.ascontiguousarray(cells, dtype=np.uint32)

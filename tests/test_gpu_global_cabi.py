@@ -108,3 +108,24 @@ def test_batched_goals_share_one_launch(pkg, oracle_mod):
         po.setGoal(gi, gj)
         po.computeEntireTotalCostMap(heap=True)
         assert rel_err(dev.download_total_cost(slot=q), po.plane("total_cost")) <= TOL_T
+
+
+def test_overlapped_total_cost_download(pkg):
+    """dymu_download_total_cost_begin/_end around a path extraction deliver the same matrix
+    as the synchronous getTotalCostMatrix read-back (inf -> -1, G.cpp:799-811)."""
+    nx, ny = 200, 150
+    dev = pkg.cuda_api.DeviceLayer(nx, ny, 1.0, 0.1)
+    dev.set_cost_map(pkg.synthetic.smooth_cost_map(ny, nx, seed=5))
+    ob = dev.download_plane_u8("obstacle")
+    goal = pkg.synthetic.free_interior_cell_near(ob, 150, 100)
+    dev.solve_total_cost([goal])
+    want = dev.download_total_cost(xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
+    got = np.full((ny, nx), np.nan)
+    dev.download_total_cost_begin(got, xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
+    wps, status = dev.extract_global_path(20.0, 20.0, 0.4, goal[0], goal[1])
+    dev.download_total_cost_end()
+    assert np.array_equal(got, want)
+    assert status == 0 and len(wps) > 10
+    # and the context keeps working afterwards
+    dev.solve_total_cost([goal])
+    assert np.array_equal(dev.download_total_cost(xform=pkg.cuda_api.XFORM_INF_TO_MINUS1), want)
