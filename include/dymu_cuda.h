@@ -147,6 +147,20 @@ int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_
  * [ranges[2k], ranges[2k+1]) of slot 0 and iterates to convergence. */
 int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges,
                       dymu_solve_stats* stats);
+/* Phase-bounded variants for pipelined domain decomposition (one GPU per row strip of a grid
+ * too large or too slow for one GPU).  The propagation of computeEntireTotalCostMap
+ * (G.cpp:443-468) is advanced by at most `max_phases` solver phases per call; the pending work
+ * lists stay on the device between calls, stats->converged tells whether anything is left.
+ *   dymu_solve_start    reset slot 0, seed the goal, run <= max_phases
+ *   dymu_solve_advance  merge the tiles covering the row ranges (halo rows whose values were
+ *                       just lowered by dymu_import_rows_min_key; n_ranges may be 0) into the
+ *                       pending work with priority `seed_key` (the smallest lowered value) and
+ *                       run <= max_phases more.  A strip without the goal starts with
+ *                       dymu_reset_total_cost and its first import. */
+int dymu_solve_start(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t max_phases,
+                     dymu_solve_stats* stats);
+int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, double seed_key,
+                       uint32_t max_phases, dymu_solve_stats* stats);
 /* resetTotalCostMap (G.cpp:473-485) without seeding a goal: every slot-0 value = +inf. */
 int dymu_reset_total_cost(dymu_ctx* ctx);
 /* Halo exchange for row-strip domain decomposition.  Rows are dense (nx doubles each).
@@ -157,6 +171,9 @@ int dymu_export_rows(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
                      int device_ptr);
 int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
                          const double* src, int device_ptr, int* changed);
+/* same, and *min_lowered = the smallest value that replaced a larger one (+inf if none) */
+int dymu_import_rows_min_key(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
+                             const double* src, int device_ptr, int* changed, double* min_lowered);
 int dymu_count_reached(dymu_ctx* ctx, uint32_t slot, uint64_t* n_finite);
 /* CLOSED-set emulation of the early stop in computeTotalCostMap (G.cpp:390): returns
  * T_stop = max over the start node and its 4 neighbours; cells with T <= T_stop are the

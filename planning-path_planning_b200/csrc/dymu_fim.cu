@@ -81,6 +81,7 @@ struct Params
     uint32_t* ctrl;
     unsigned long long* stats;
     int inner_cap, max_outer;
+    int outer0;                 // rotation of the three lists at entry (phase-bounded solves)
     double band;                // tiles with key > min key + band wait (inf = plain FIM)
 };
 
@@ -209,10 +210,10 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 #else
 #define PC_MARK(acc)
 #endif
-    int outer = 0;
+    int outer = p.outer0;
     bool converged = false;
 
-    for (; outer < p.max_outer; ++outer)
+    for (; outer < p.outer0 + p.max_outer; ++outer)
     {
         const int cur = outer % 3, nxt = (outer + 1) % 3, old = (outer + 2) % 3;
         const uint32_t n_active = ld_volatile_u32(&p.ctrl[cur]);
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
         if (n_inner) atomicAdd(&p.stats[5], n_inner);
         if (blockIdx.x == 0)
         {
-            p.stats[2] = (unsigned long long)outer;
+            p.stats[2] = (unsigned long long)(outer - p.outer0);
             p.stats[3] = converged ? 1ull : 0ull;
         }
     }
@@ -578,12 +579,27 @@ __global__ void k_seed_rows(uint32_t ntx, const uint32_t* tile_rows, uint32_t n_
     }
 }
 
+// adds every tile of the given tile rows to a list that may already hold pending tiles
+__global__ void k_seed_rows_add(uint32_t ntx, const uint32_t* tile_rows, uint32_t n_tile_rows, uint32_t* list,
+                                uint32_t* flag, unsigned long long* key, unsigned long long* gmin_cur,
+                                uint32_t* count_cur, unsigned long long seed_key)
+{
+    uint32_t n = n_tile_rows * ntx;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint32_t tile_id = tile_rows[q / ntx] * ntx + q % ntx;
+    atomicMin(&key[tile_id], seed_key);
+    if (atomicOr(&flag[tile_id], kFull) == 0) list[atomicAdd(count_cur, 1u)] = tile_id;
+    if (q == 0) atomicMin(gmin_cur, seed_key);
+}
+
 __global__ void k_import_rows_min(double* T, uint32_t pitch, uint32_t nx, uint32_t j0, uint32_t n_rows,
-                                  const double* src, int* changed)
+                                  const double* src, int* changed, unsigned long long* min_lowered)
 {
     size_t total = (size_t)nx * n_rows;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     int any = 0;
+    unsigned long long lowest = kNoKey;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride)
     {
         uint32_t r = (uint32_t)(k / nx), i = (uint32_t)(k % nx);
@@ -593,9 +609,18 @@ __global__ void k_import_rows_min(double* T, uint32_t pitch, uint32_t nx, uint32
         {
             *t = v;
             any = 1;
+            lowest = min(lowest, key_of(v));
         }
     }
-    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *changed = 1;
+    if (__any_sync(0xffffffffu, any))
+    {
+        for (int o = 16; o > 0; o >>= 1) lowest = min(lowest, __shfl_xor_sync(0xffffffffu, lowest, o));
+        if ((threadIdx.x & 31) == 0)
+        {
+            *changed = 1;
+            atomicMin(min_lowered, lowest);
+        }
+    }
 }
 
 template <int TILE, int MODE> int launch_fim(dymu_ctx* ctx, Params& prm, size_t total_tiles)
@@ -687,17 +712,40 @@ int dymu_internal_fim_reset(dymu_ctx* ctx, dymu_fim_work* w);
 int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_stats* stats)
 {
     if (L.tile != 32) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unsupported tile edge %d", L.tile);
+    if (L.resume && L.work->pending)
+    {
+        // continue with the lists the previous launch left behind; new seeds are merged in
+        dymu_fim_work* w0 = L.work;
+        const int cur = w0->rot;
+        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w0->ctrl + 6, 0, 2 * sizeof(uint32_t), ctx->stream));
+        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w0->stats, 0, 16 * sizeof(unsigned long long), ctx->stream));
+        if (L.seed_kind == 1 && L.n_initial)
+        {
+            k_seed_rows_add<<<dymu_div_up(L.n_initial * L.ntx, 128), 128, 0, ctx->stream>>>(
+                L.ntx, L.seed_data, L.n_initial, w0->list[cur], w0->flag[cur], w0->key[cur], w0->gmin + cur,
+                w0->ctrl + cur, (unsigned long long)__builtin_bit_cast(long long, L.seed_key));
+            ctx->launches++;
+            DYMU_CUDA_TRY(ctx, cudaGetLastError());
+        }
+        else if (L.seed_kind != 3 && L.seed_kind != 1)
+            DYMU_FAIL(ctx, DYMU_ERR_ARG, "a resumed solve takes tile-row seeds only");
+    }
+    else
     {
         dymu_fim_work* w0 = L.work;
         DYMU_TRY(dymu_internal_fim_reset(ctx, w0));
+        w0->rot = 0;
         if (L.seed_kind == 0)
             k_seed<<<dymu_div_up(L.n_initial, 128), 128, 0, ctx->stream>>>(
                 L.T, L.slot_stride, L.pitch, L.ntx, L.nty, L.tile, L.seed_data, L.n_initial, w0->list[0],
                 w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
         else if (L.seed_kind == 1)
-            k_seed_rows<<<dymu_div_up(L.n_initial * L.ntx, 128), 128, 0, ctx->stream>>>(
-                L.ntx, L.seed_data, L.n_initial, w0->list[0], w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
-        else
+        {
+            if (L.n_initial)
+                k_seed_rows<<<dymu_div_up(L.n_initial * L.ntx, 128), 128, 0, ctx->stream>>>(
+                    L.ntx, L.seed_data, L.n_initial, w0->list[0], w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
+        }
+        else if (L.seed_kind == 2)
             k_seed_all<<<dymu_div_up(L.ntx * L.nty, 128), 128, 0, ctx->stream>>>(
                 L.ntx * L.nty, w0->list[0], w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
         ctx->launches++;
@@ -754,6 +802,8 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     prm.max_outer = 64 * (int)(L.ntx + L.nty) + 4096;
     if (const char* e = getenv("DYMU_FIM_MAX_OUTER"))
         if (atoi(e) > 0) prm.max_outer = atoi(e);
+    if (L.max_phases > 0) prm.max_outer = (int)L.max_phases;
+    prm.outer0 = w->rot;
     size_t total_tiles = (size_t)L.ntx * L.nty * L.nprob;
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     int rc;
@@ -810,7 +860,9 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
         stats->inner_iterations = h[5];
         DYMU_CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev1, ctx->ev2));
     }
-    if (!h[3])
+    w->rot = (int)((prm.outer0 + h[2]) % 3);
+    w->pending = !h[3];
+    if (!h[3] && L.max_phases == 0)
         DYMU_FAIL(ctx, DYMU_ERR_NOCONV, "tile FIM hit the outer-iteration cap (%d) before converging",
                   prm.max_outer);
     return DYMU_OK;
@@ -887,8 +939,8 @@ int dymu_reserve_slots(dymu_ctx* ctx, uint32_t n_slots)
     return DYMU_OK;
 }
 
-int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_i,
-                          const uint32_t* goal_j, dymu_solve_stats* stats)
+static int solve_total_cost_impl(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_i,
+                                 const uint32_t* goal_j, uint32_t max_phases, dymu_solve_stats* stats)
 {
     if (!ctx || !goal_i || !goal_j || n_goals < 1 || n_goals > ctx->n_slots) return DYMU_ERR_ARG;
     if (!ctx->have_cost) DYMU_FAIL(ctx, DYMU_ERR_STATE, "no cost map: call dymu_set_cost_map / dymu_compute_cost_map first");
@@ -913,6 +965,7 @@ int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_
     L.ntx = ctx->ntx; L.nty = ctx->nty; L.nprob = n_goals; L.mode = 0; L.tile = (int)ctx->tile;
     L.work = &ctx->work; L.n_initial = n_goals; L.band = ctx->fim_band;
     L.seed_kind = 0; L.seed_data = (const uint32_t*)ctx->d_scratch;
+    L.max_phases = max_phases;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     int rc = dymu_internal_fim_run(ctx, L, &local);
@@ -921,14 +974,38 @@ int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_
         cudaEventElapsedTime(&local.reset_ms, ctx->ev0, ctx->ev1);
         if (stats) stats[0] = local;
     }
-    ctx->solved = (rc == DYMU_OK);
+    ctx->solved = (rc == DYMU_OK) && local.converged;
     return rc;
 }
 
-int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, dymu_solve_stats* stats)
+int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_i,
+                          const uint32_t* goal_j, dymu_solve_stats* stats)
 {
-    if (!ctx || !ranges || n_ranges == 0) return DYMU_ERR_ARG;
+    return solve_total_cost_impl(ctx, n_goals, goal_i, goal_j, 0, stats);
+}
+
+int dymu_solve_start(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t max_phases,
+                     dymu_solve_stats* stats)
+{
+    if (max_phases == 0) return DYMU_ERR_ARG;
+    return solve_total_cost_impl(ctx, 1, &goal_i, &goal_j, max_phases, stats);
+}
+
+static int solve_resume_impl(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, bool keep_pending,
+                             double seed_key, uint32_t max_phases, dymu_solve_stats* stats)
+{
+    if (!ctx || (!ranges && n_ranges)) return DYMU_ERR_ARG;
     if (!ctx->have_cost) DYMU_FAIL(ctx, DYMU_ERR_STATE, "no cost map");
+    if (n_ranges == 0 && !(keep_pending && ctx->work.pending))
+    {
+        // nothing queued and nothing new: the plane is at its fixed point
+        if (stats)
+        {
+            memset(stats, 0, sizeof(*stats));
+            stats->converged = 1;
+        }
+        return DYMU_OK;
+    }
     DYMU_TRY(dymu_internal_refresh_ceff(ctx));
     // distinct tile rows covered by the ranges
     uint32_t* h_rows = (uint32_t*)malloc(sizeof(uint32_t) * ctx->nty);
@@ -962,7 +1039,10 @@ int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, 
     L.T = ctx->T; L.slot_stride = (size_t)ctx->pitch * ctx->rows; L.C = ctx->ceff;
     L.pitch = ctx->pitch; L.rows = ctx->rows; L.ntx = ctx->ntx; L.nty = ctx->nty; L.nprob = 1;
     L.mode = 0; L.tile = (int)ctx->tile; L.work = &ctx->work; L.n_initial = n_rows; L.band = ctx->fim_band;
-    L.seed_kind = 1; L.seed_data = (const uint32_t*)ctx->d_scratch;
+    L.seed_kind = n_rows ? 1 : 3; L.seed_data = (const uint32_t*)ctx->d_scratch;
+    L.resume = keep_pending;
+    L.max_phases = max_phases;
+    L.seed_key = seed_key;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     rc = dymu_internal_fim_run(ctx, L, &local);
@@ -970,10 +1050,24 @@ int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, 
     return rc;
 }
 
+int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, dymu_solve_stats* stats)
+{
+    if (!ranges || n_ranges == 0) return DYMU_ERR_ARG;
+    return solve_resume_impl(ctx, ranges, n_ranges, false, 0.0, 0, stats);
+}
+
+int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, double seed_key,
+                       uint32_t max_phases, dymu_solve_stats* stats)
+{
+    if (max_phases == 0 || !(seed_key >= 0.0)) return DYMU_ERR_ARG;
+    return solve_resume_impl(ctx, ranges, n_ranges, true, seed_key, max_phases, stats);
+}
+
 int dymu_reset_total_cost(dymu_ctx* ctx)
 {
     if (!ctx) return DYMU_ERR_ARG;
     ctx->solved = false;
+    ctx->work.pending = false;
     return dymu_internal_fill(ctx, ctx->T, 1.0 / 0.0, (size_t)ctx->pitch * ctx->rows);
 }
 
@@ -991,8 +1085,8 @@ int dymu_export_rows(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
     return DYMU_OK;
 }
 
-int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
-                         const double* src, int device_ptr, int* changed)
+static int import_rows_impl(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows, const double* src,
+                            int device_ptr, int* changed, double* min_lowered)
 {
     if (!ctx || !src || !changed || slot >= ctx->n_slots || n_rows == 0
         || (uint64_t)j0 + n_rows > ctx->ny)
@@ -1000,8 +1094,10 @@ int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_r
     size_t bytes = (size_t)ctx->nx * n_rows * sizeof(double);
     DYMU_TRY(dymu_internal_scratch(ctx, bytes + 64, device_ptr ? 64 : bytes + 64));
     int* d_flag = (int*)ctx->d_scratch;
+    unsigned long long* d_min = (unsigned long long*)((char*)ctx->d_scratch + 8);
     const double* d_src = src;
-    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, 8, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d_min, 0xFF, 8, ctx->stream));
     if (!device_ptr)
     {
         double* stage = (double*)((char*)ctx->d_scratch + 64);
@@ -1014,14 +1110,34 @@ int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_r
     int grid = (int)((total + 255) / 256);
     if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
     k_import_rows_min<<<grid, 256, 0, ctx->stream>>>(ctx->T + (size_t)slot * ctx->pitch * ctx->rows,
-                                                     ctx->pitch, ctx->nx, j0, n_rows, d_src, d_flag);
+                                                     ctx->pitch, ctx->nx, j0, n_rows, d_src, d_flag, d_min);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
-    int h = 0;
-    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long h[2] = {0, 0};
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_flag, 16, cudaMemcpyDeviceToHost, ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    *changed = h;
+    *changed = (int)(h[0] & 0xffffffffu);
+    if (min_lowered)
+    {
+        long long bits = (long long)h[1];
+        double v;
+        memcpy(&v, &bits, sizeof(v));
+        *min_lowered = *changed ? v : 1.0 / 0.0;
+    }
     return DYMU_OK;
+}
+
+int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
+                         const double* src, int device_ptr, int* changed)
+{
+    return import_rows_impl(ctx, slot, j0, n_rows, src, device_ptr, changed, nullptr);
+}
+
+int dymu_import_rows_min_key(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
+                             const double* src, int device_ptr, int* changed, double* min_lowered)
+{
+    if (!min_lowered) return DYMU_ERR_ARG;
+    return import_rows_impl(ctx, slot, j0, n_rows, src, device_ptr, changed, min_lowered);
 }
 
 int dymu_stop_threshold(dymu_ctx* ctx, uint32_t slot, uint32_t start_i, uint32_t start_j,

@@ -65,10 +65,15 @@ _SIG = {
     "dymu_solve_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _u32p, _u32p,
                                         C.POINTER(SolveStats)]),
     "dymu_solve_resume": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, C.POINTER(SolveStats)]),
+    "dymu_solve_start": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(SolveStats)]),
+    "dymu_solve_advance": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, C.c_double, C.c_uint32,
+                                     C.POINTER(SolveStats)]),
     "dymu_reset_total_cost": (C.c_int, [C.c_void_p]),
     "dymu_export_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]),
     "dymu_import_rows_min": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                        C.c_int, C.POINTER(C.c_int)]),
+    "dymu_import_rows_min_key": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                           C.c_int, C.POINTER(C.c_int), _dp]),
     "dymu_count_reached": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
     "dymu_stop_threshold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _dp]),
     "dymu_download_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_size_t, C.c_int]),
@@ -276,6 +281,20 @@ class DeviceLayer:
                                             C.byref(st)))
         return st.as_dict()
 
+    def solve_start(self, goal, max_phases):
+        """Seed the goal and run at most max_phases solver phases; stats['converged'] == 0 means
+        work is pending on the device (continue with solve_advance)."""
+        st = SolveStats()
+        self._chk(self._l.dymu_solve_start(self._h, int(goal[0]), int(goal[1]), int(max_phases), C.byref(st)))
+        return st.as_dict()
+
+    def solve_advance(self, ranges, seed_key, max_phases):
+        r = np.ascontiguousarray(list(ranges), dtype=np.uint32).reshape(-1, 2)
+        st = SolveStats()
+        self._chk(self._l.dymu_solve_advance(self._h, r.ctypes.data_as(_u32p), r.shape[0], float(seed_key),
+                                             int(max_phases), C.byref(st)))
+        return st.as_dict()
+
     def reset_total_cost(self):
         self._chk(self._l.dymu_reset_total_cost(self._h))
 
@@ -288,6 +307,14 @@ class DeviceLayer:
         self._chk(self._l.dymu_import_rows_min(self._h, slot, j0, n_rows, C.c_void_p(src_ptr),
                                                int(device_ptr), C.byref(ch)))
         return bool(ch.value)
+
+    def import_rows_min_key(self, j0, n_rows, src_ptr, device_ptr, slot=0):
+        """-> (changed, smallest value that replaced a larger one or +inf)."""
+        ch = C.c_int()
+        lo = C.c_double()
+        self._chk(self._l.dymu_import_rows_min_key(self._h, slot, j0, n_rows, C.c_void_p(src_ptr),
+                                                   int(device_ptr), C.byref(ch), C.byref(lo)))
+        return bool(ch.value), float(lo.value)
 
     def count_reached(self, slot=0):
         n = C.c_uint64()

@@ -11,6 +11,12 @@ Two cases shard naturally:
   carry C_eff = +inf, so they are never updated locally and act as Dirichlet data; values
   only ever decrease, so the iteration converges to the single-grid fixed point.
 
+``dd_solve_pipelined`` is the same decomposition without the "converge, then talk" rhythm:
+every rank advances its strip by a bounded number of solver phases per round
+(``dymu_solve_start`` / ``dymu_solve_advance`` keep the pending work on the device), so a
+neighbour starts as soon as the wave front crosses the cut instead of after the whole strip
+behind it has converged.
+
 The driver is written against two small interfaces so that the very same control flow runs
 on GPUs (``CudaStrip`` + torch.distributed/NCCL) and in the CPU test-suite (a numpy strip
 solver + gloo).
@@ -143,6 +149,39 @@ class CudaStrip:
     def resume(self, ranges):
         self.stats.append(self.dev.solve_resume(ranges))
 
+    # -- phase-bounded protocol (dd_solve_pipelined) ------------------------------------
+    def start_bounded(self, goal_global, phases):
+        """Like start(), but stops after `phases` solver phases.  Returns True while work is
+        pending on the device."""
+        gi, gj = goal_global
+        if self.layout.owns(gj):
+            st = self.dev.solve_start((gi, self.layout.local_row(gj)), phases)
+            self.stats.append(st)
+            return not st["converged"]
+        self.dev.reset_total_cost()
+        return False
+
+    def absorb_keyed(self, from_above, from_below):
+        """absorb() that also returns the smallest value a ghost row was lowered to: the
+        priority the re-activated tiles get among the pending ones."""
+        lay, ranges, key = self.layout, [], float("inf")
+        if from_above is not None:
+            ch, lo = self.dev.import_rows_min_key(0, 1, from_above.data_ptr(), True)
+            if ch:
+                ranges.append((0, 2))
+                key = min(key, lo)
+        if from_below is not None:
+            ch, lo = self.dev.import_rows_min_key(lay.ny_local - 1, 1, from_below.data_ptr(), True)
+            if ch:
+                ranges.append((lay.ny_local - 2, lay.ny_local))
+                key = min(key, lo)
+        return ranges, key
+
+    def advance(self, ranges, key, phases):
+        st = self.dev.solve_advance(ranges, key if ranges else 0.0, phases)
+        self.stats.append(st)
+        return not st["converged"]
+
     def own_rows(self):
         lay = self.layout
         T = self.dev.download_total_cost()
@@ -162,6 +201,24 @@ def dd_solve(strip, comm, goal_global, max_rounds=10000):
             break
         if ranges:
             strip.resume(ranges)
+    return rounds
+
+
+def dd_solve_pipelined(strip, comm, goal_global, phases_per_round=16, max_rounds=1000000):
+    """Domain-decomposed solve with bounded work per exchange round: every rank runs at most
+    `phases_per_round` solver phases, trades boundary rows, merges what it received into its
+    pending work, and the loop ends when no rank has pending work or fresh halo values.
+    Returns the number of rounds."""
+    pending = strip.start_bounded(goal_global, phases_per_round)
+    rounds = 0
+    while rounds < max_rounds:
+        top, bottom = strip.boundary_rows()
+        from_above, from_below = comm.exchange(top, bottom)
+        ranges, key = strip.absorb_keyed(from_above, from_below)
+        rounds += 1
+        if not comm.any(bool(ranges) or pending):
+            break
+        pending = strip.advance(ranges, key, phases_per_round)
     return rounds
 
 
@@ -185,4 +242,22 @@ def dd_solve_lockstep(strips, goal_global, max_rounds=10000):
         for s, ranges in zip(strips, todo):
             if ranges:
                 s.resume(ranges)
+    return rounds
+
+
+def dd_solve_lockstep_pipelined(strips, goal_global, phases_per_round=16, max_rounds=1000000):
+    """dd_solve_pipelined with all strips in one process (see dd_solve_lockstep)."""
+    pending = [s.start_bounded(goal_global, phases_per_round) for s in strips]
+    rounds = 0
+    while rounds < max_rounds:
+        rows = [tuple(r.clone() for r in s.boundary_rows()) for s in strips]
+        rounds += 1
+        todo = []
+        for k, s in enumerate(strips):
+            from_above = rows[k - 1][1] if k > 0 else None
+            from_below = rows[k + 1][0] if k + 1 < len(strips) else None
+            todo.append(s.absorb_keyed(from_above, from_below))
+        if not any(pending) and not any(r for r, _ in todo):
+            break
+        pending = [s.advance(r, key, phases_per_round) for s, (r, key) in zip(strips, todo)]
     return rounds

@@ -19,6 +19,8 @@ ap.add_argument("--size", dest="n", type=int, default=16384)
 ap.add_argument("--base", type=int, default=4096, help="edge of the periodic fBm cost tile")
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--phases", type=int, default=0,
+                help="> 0: pipelined exchange every that many solver phases (dd_solve_pipelined)")
 a = ap.parse_args()
 
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -44,7 +46,8 @@ for r in range(a.reps):
         dist.barrier()
     t0 = time.perf_counter()
     if world > 1:
-        rounds = sh.dd_solve(strip, comm, goal)
+        rounds = sh.dd_solve_pipelined(strip, comm, goal, a.phases) if a.phases > 0 \
+            else sh.dd_solve(strip, comm, goal)
     else:
         strip.start(goal)
         rounds = 1
@@ -73,6 +76,6 @@ if a.verify:
 if rank == 0:
     print(json.dumps({"workload": "%dx%d single grid, row strips" % (n, n), "n_gpus": world,
                       "wall_ms": float(t[0]) * 1e3, "max_rank_kernel_ms": float(t[1]),
-                      "exchange_rounds": rounds, "verified": ok}))
+                      "exchange_rounds": rounds, "phases_per_round": a.phases, "verified": ok}))
 if world > 1:
     dist.destroy_process_group()

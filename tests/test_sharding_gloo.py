@@ -30,9 +30,14 @@ class NumpyStrip:
         self.C = np.where(cost > 0, 1.0 * cost * (2 + 0.0 - 1.0), np.inf)
         self.T = np.full(cost.shape, np.inf)
 
-    def _relax(self):
+    def _relax(self, max_sweeps=None):
+        """Returns True if it stopped at the sweep budget with changes still happening."""
         T, C = self.T, self.C
+        sweeps = 0
         while True:
+            if max_sweeps is not None and sweeps >= max_sweeps:
+                return True
+            sweeps += 1
             P = np.pad(T, 1, constant_values=np.inf)
             Tx = np.minimum(P[1:-1, :-2], P[1:-1, 2:])
             Ty = np.minimum(P[:-2, 1:-1], P[2:, 1:-1])
@@ -40,7 +45,7 @@ class NumpyStrip:
                 Tn = _eikonal(Tx, Ty, C)
             better = np.isfinite(C) & (Tn < T)
             if not better.any():
-                return
+                return False
             T[better] = Tn[better]
 
     def start(self, goal_global):
@@ -70,12 +75,35 @@ class NumpyStrip:
     def resume(self, ranges):
         self._relax()
 
+    # phase-bounded protocol: a "phase" is one Jacobi sweep here
+    def start_bounded(self, goal_global, phases):
+        gi, gj = goal_global
+        self.T[...] = np.inf
+        if self.layout.owns(gj):
+            self.T[self.layout.local_row(gj), gi] = 0.0
+            return self._relax(phases)
+        return False
+
+    def absorb_keyed(self, from_above, from_below):
+        before = [None if s is None else self.T[r].copy()
+                  for r, s in ((0, from_above), (self.layout.ny_local - 1, from_below))]
+        ranges = self.absorb(from_above, from_below)
+        key = np.inf
+        for (r, s), old in zip(((0, from_above), (self.layout.ny_local - 1, from_below)), before):
+            if s is not None and (self.T[r] < old).any():
+                key = min(key, float(self.T[r][self.T[r] < old].min()))
+        return ranges, key
+
+    def advance(self, ranges, key, phases):
+        assert (not ranges) or np.isfinite(key)
+        return self._relax(phases)
+
     def own_rows(self):
         lay = self.layout
         return self.T[lay.first_own:lay.last_own + 1]
 
 
-def _worker(rank, world, port, cost, goal, out_dir):
+def _worker(rank, world, port, cost, goal, out_dir, pipelined=False):
     sys.path.insert(0, ROOT)
     import dymu_b200
     sh = dymu_b200.load().sharding
@@ -85,19 +113,22 @@ def _worker(rank, world, port, cost, goal, out_dir):
     lay = sh.StripLayout(cost.shape[0], world, rank, align=8)
     strip = NumpyStrip(lay, cost[lay.r0:lay.r1])
     comm = sh.TorchComm(rank, world, torch.device("cpu"))
-    rounds = sh.dd_solve(strip, comm, goal)
+    rounds = sh.dd_solve_pipelined(strip, comm, goal, phases_per_round=7) if pipelined \
+        else sh.dd_solve(strip, comm, goal)
     np.save(os.path.join(out_dir, "T_%d.npy" % rank), strip.own_rows())
     np.save(os.path.join(out_dir, "rounds_%d.npy" % rank), np.array([rounds, lay.r0, lay.r1]))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,port", [(2, 29611), (3, 29612)])
-def test_domain_decomposition_matches_single_grid(pkg, oracle_mod, tmp_path, world, port):
+@pytest.mark.parametrize("world,port,pipelined", [(2, 29611, False), (3, 29612, False),
+                                                  (2, 29613, True), (3, 29614, True)])
+def test_domain_decomposition_matches_single_grid(pkg, oracle_mod, tmp_path, world, port, pipelined):
     ny, nx = 72, 56
     cost = pkg.synthetic.smooth_cost_map(ny, nx, seed=5, obstacle_fraction=0.05)
     ob = cost <= 0
     gi, gj = pkg.synthetic.free_interior_cell_near(ob, 40, 12)   # goal inside the first strip
-    mp.spawn(_worker, args=(world, port, cost, (gi, gj), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, cost, (gi, gj), str(tmp_path), pipelined), nprocs=world,
+             join=True)
     parts = [np.load(tmp_path / ("T_%d.npy" % r)) for r in range(world)]
     T = np.vstack(parts)
     po = oracle_mod.Port(1.0, 1.5, 2.0, 1)
