@@ -273,6 +273,17 @@ def cpu_baseline_leg(pkg, elev, terr, lut, slopes, locs, n):
 # ---------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------
+def _measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_fim launch on this workload, from the
+    committed `ncu --set full` capture (profiles/); None when the summary is not there."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                               "r1_k_fim_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def run_b200(args):
     import torch
     import dymu_b200
@@ -398,7 +409,7 @@ def run_b200(args):
         "roofline": {
             "bound": "hbm", "kernel": "k_fim<%d,0> (tile FIM sweep)" % tile,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": _measured_traffic(), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes,
             "definition": "tile activations x %d^2 cells x 24 B (read T, read C_eff, write T) / "
                           "kernel time; the kernel iterates in shared memory between load and "

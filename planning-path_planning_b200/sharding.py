@@ -209,16 +209,26 @@ def dd_solve_pipelined(strip, comm, goal_global, phases_per_round=16, max_rounds
     `phases_per_round` solver phases, trades boundary rows, merges what it received into its
     pending work, and the loop ends when no rank has pending work or fresh halo values.
     Returns the number of rounds."""
-    pending = strip.start_bounded(goal_global, phases_per_round)
+    import time
+    lap = {"advance": 0.0, "export": 0.0, "exchange": 0.0, "absorb": 0.0, "vote": 0.0}
+
+    def timed(name, fn, *a):
+        t0 = time.perf_counter()
+        out = fn(*a)
+        lap[name] += time.perf_counter() - t0
+        return out
+
+    pending = timed("advance", strip.start_bounded, goal_global, phases_per_round)
     rounds = 0
     while rounds < max_rounds:
-        top, bottom = strip.boundary_rows()
-        from_above, from_below = comm.exchange(top, bottom)
-        ranges, key = strip.absorb_keyed(from_above, from_below)
+        top, bottom = timed("export", strip.boundary_rows)
+        from_above, from_below = timed("exchange", comm.exchange, top, bottom)
+        ranges, key = timed("absorb", strip.absorb_keyed, from_above, from_below)
         rounds += 1
-        if not comm.any(bool(ranges) or pending):
+        if not timed("vote", comm.any, bool(ranges) or pending):
             break
-        pending = strip.advance(ranges, key, phases_per_round)
+        pending = timed("advance", strip.advance, ranges, key, phases_per_round)
+    strip.laps = lap
     return rounds
 
 

@@ -73,6 +73,9 @@ if a.verify:
     if world > 1:
         dist.all_reduce(good, op=dist.ReduceOp.MIN)
     ok = bool(good.item())
+if rank == 0 and getattr(strip, "laps", None):
+    print("host wall per stage, last solve (ms):", {k: round(v * 1e3, 2) for k, v in strip.laps.items()},
+          file=sys.stderr)
 if rank == 0:
     print(json.dumps({"workload": "%dx%d single grid, row strips" % (n, n), "n_gpus": world,
                       "wall_ms": float(t[0]) * 1e3, "max_rank_kernel_ms": float(t[1]),
