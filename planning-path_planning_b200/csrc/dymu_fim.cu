@@ -38,16 +38,21 @@ namespace
 {
 template <int TILE> struct Cfg
 {
-    static_assert(TILE == 32, "16 warps x one 8x8 block each");
-    static constexpr int THREADS = 512;       // 16 warps
-    static constexpr int WARPS = THREADS / 32;
+    static_assert(TILE == 32, "4 x 4 blocks of 8 x 8 cells");
+#ifndef DYMU_FIM_WARPS
+#define DYMU_FIM_WARPS 16
+#endif
+    static constexpr int WARPS = DYMU_FIM_WARPS;  // 16: one block per warp, 8: two blocks per warp
+    static_assert(WARPS == 16 || WARPS == 8, "warps per tile");
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int NB = 16 / WARPS;         // blocks per warp: block b = warp + h * WARPS
     static constexpr int BX = TILE / 8;       // 4 x 4 blocks of 8 x 8 cells, block w <-> warp w
     static constexpr int BY = TILE / 8;
     // row pitch of the shared arrays in doubles; PITCH % 16 == 8 makes consecutive 8-double
     // rows of a block fall into disjoint bank groups (conflict-free 64-bit access)
     static constexpr int PITCH = TILE + 8;
     static constexpr int CPT = TILE * TILE / THREADS;  // cells per thread in load/store = 2
-    static constexpr int MIN_CTAS = 2;
+    static constexpr int MIN_CTAS = 32 / WARPS;   // 1024 threads per SM either way
     static constexpr size_t SMEM = sizeof(double) * ((TILE + 2) * PITCH + TILE * PITCH);
 };
 
@@ -360,16 +365,25 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             // lane (lx, ly) owns the cells (lx, ly) and (lx, ly + 4) of it, whose two update
             // chains are independent and interleave in the in-order issue stream.  A sweep is
             // therefore one visit per warp, whatever the number of dirty blocks.
-            const int bx = warp & 3, by = warp >> 2;
             const int lx = lane & 7, ly = lane >> 3;
-            const int oA = (by * 8 + ly + 1) * P + bx * 8 + lx + 1, oB = oA + 4 * P;
-            const double cA = Cs[(by * 8 + ly) * P + bx * 8 + lx], cB = Cs[(by * 8 + ly + 4) * P + bx * 8 + lx];
-            const uint32_t my_bit = 1u << warp;
-            // neighbour-block bits (0 where the block sits on the tile edge) and which tile
-            // edges this block touches
-            const uint32_t bitL = bx > 0 ? my_bit >> 1 : 0u, bitR = bx < K::BX - 1 ? my_bit << 1 : 0u;
-            const uint32_t bitU = by > 0 ? my_bit >> 4 : 0u, bitD = by < K::BY - 1 ? my_bit << 4 : 0u;
-            const bool at_edge = !(bitL && bitR && bitU && bitD);
+            int oA[K::NB];
+            double cA[K::NB], cB[K::NB];
+            uint32_t my_bit[K::NB], bitL[K::NB], bitR[K::NB], bitU[K::NB], bitD[K::NB];
+#pragma unroll
+            for (int h = 0; h < K::NB; ++h)
+            {
+                const int b = warp + h * K::WARPS;
+                const int bx = b & 3, by = b >> 2;
+                oA[h] = (by * 8 + ly + 1) * P + bx * 8 + lx + 1;
+                cA[h] = Cs[(by * 8 + ly) * P + bx * 8 + lx];
+                cB[h] = Cs[(by * 8 + ly + 4) * P + bx * 8 + lx];
+                my_bit[h] = 1u << b;
+                // neighbour-block bits (0 where the block sits on the tile edge)
+                bitL[h] = bx > 0 ? my_bit[h] >> 1 : 0u;
+                bitR[h] = bx < K::BX - 1 ? my_bit[h] << 1 : 0u;
+                bitU[h] = by > 0 ? my_bit[h] >> 4 : 0u;
+                bitD[h] = by < K::BY - 1 ? my_bit[h] << 4 : 0u;
+            }
             int it = 0;
             uint32_t visits = 0;
             uint32_t* m_cur = &dmask[0];
@@ -379,35 +393,38 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             while (m != 0 && it < p.inner_cap)
             {
                 if (tid == 0) *m_old = 0;
-                if (m & my_bit)
+#pragma unroll
+                for (int h = 0; h < K::NB; ++h)
                 {
-                    const double tA = Ts[oA], lA = Ts[oA - 1], rA = Ts[oA + 1], uA = Ts[oA - P], dA = Ts[oA + P];
-                    const double tB = Ts[oB], lB = Ts[oB - 1], rB = Ts[oB + 1], uB = Ts[oB - P], dB = Ts[oB + P];
+                    if (!(m & my_bit[h])) continue;
+                    const int a = oA[h], b = a + 4 * P;
+                    const double tA = Ts[a], lA = Ts[a - 1], rA = Ts[a + 1], uA = Ts[a - P], dA = Ts[a + P];
+                    const double tB = Ts[b], lB = Ts[b - 1], rB = Ts[b + 1], uB = Ts[b - P], dB = Ts[b + P];
                     double nA, nB;
-                    const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA, nA);
-                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB, nB);
-                    if (chA) Ts[oA] = nA;
-                    if (chB) Ts[oB] = nB;
+                    const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], nA);
+                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], nB);
+                    if (chA) Ts[a] = nA;
+                    if (chB) Ts[b] = nB;
                     const uint32_t mA = __ballot_sync(0xffffffffu, chA);
                     const uint32_t mB = __ballot_sync(0xffffffffu, chB);
                     const uint32_t mAB = mA | mB;
                     visits += 2;
                     if (mAB)
                     {
-                        uint32_t bits = my_bit;
-                        bits |= (mAB & kLeftLanes) ? bitL : 0u;
-                        bits |= (mAB & kRightLanes) ? bitR : 0u;
-                        bits |= (mA & kTopLanes) ? bitU : 0u;
-                        bits |= (mB & kBottomLanes) ? bitD : 0u;
+                        uint32_t bits = my_bit[h];
+                        bits |= (mAB & kLeftLanes) ? bitL[h] : 0u;
+                        bits |= (mAB & kRightLanes) ? bitR[h] : 0u;
+                        bits |= (mA & kTopLanes) ? bitU[h] : 0u;
+                        bits |= (mB & kBottomLanes) ? bitD[h] : 0u;
                         if (lane == 0)
                         {
                             atomicOr(m_nxt, bits);
-                            if (at_edge)
+                            if (!(bitL[h] && bitR[h] && bitU[h] && bitD[h]))
                             {
-                                if ((mAB & kLeftLanes) && !bitL) edge_changed[2] = 1;
-                                if ((mAB & kRightLanes) && !bitR) edge_changed[3] = 1;
-                                if ((mA & kTopLanes) && !bitU) edge_changed[0] = 1;
-                                if ((mB & kBottomLanes) && !bitD) edge_changed[1] = 1;
+                                if ((mAB & kLeftLanes) && !bitL[h]) edge_changed[2] = 1;
+                                if ((mAB & kRightLanes) && !bitR[h]) edge_changed[3] = 1;
+                                if ((mA & kTopLanes) && !bitU[h]) edge_changed[0] = 1;
+                                if ((mB & kBottomLanes) && !bitD[h]) edge_changed[1] = 1;
                             }
                         }
                     }

@@ -1,0 +1,29 @@
+"""Developer probe: sweep of the priority-band width and the per-activation sweep cap."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dymu_b200
+pkg = dymu_b200.load(); syn = pkg.synthetic
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+elev, terr = syn.mars_dem(n, n, seed=20261018)
+lut, slopes, locs = syn.default_lut()
+goal = None
+for inner in (32, 48, 64, 96):
+    for band in (1.5, 2.0, 2.5, 3.0, 4.0, 6.0):
+        os.environ["DYMU_FIM_BAND"] = str(band)
+        os.environ["DYMU_FIM_INNER"] = str(inner)
+        dev = pkg.cuda_api.DeviceLayer(n, n, 1.0, 0.1)
+        dev.compute_cost_map(lut, slopes, len(locs), elev, terr)
+        if goal is None:
+            ob = dev.download_plane_u8("obstacle")
+            goal = syn.free_interior_cell_near(ob, n // 2, n // 2)
+        best = None
+        for rep in range(3):
+            st = dev.solve_total_cost([goal])
+            if best is None or st["kernel_ms"] < best["kernel_ms"]:
+                best = st
+        print("inner %3d band %.1f: %.2f ms, %d phases, %d activations, %.1f sweeps/activation" %
+              (inner, band, best["kernel_ms"], best["outer_iterations"], best["tile_activations"],
+               best["inner_iterations"] / max(best["tile_activations"], 1)), flush=True)
+        del dev
