@@ -86,6 +86,7 @@ struct Params
     uint32_t* ctrl;
     unsigned long long* stats;
     int inner_cap, max_outer;
+    int phase_budget, min_slice;  // sweeps a CTA may spend per phase; smallest slice worth a tile load
     int outer0;                 // rotation of the three lists at entry (phase-bounded solves)
     double band;                // tiles with key > min key + band wait (inf = plain FIM)
 };
@@ -97,6 +98,10 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)
 {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void smem_or(uint32_t* p, uint32_t v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 // non-negative doubles order like their bit patterns, so atomicMin on the bits is a min
@@ -195,12 +200,40 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     double* Ts = reinterpret_cast<double*>(smem_raw);            // (TILE+2) x P, 1-cell halo
     double* Cs = Ts + (TILE + 2) * P;                            // TILE x P
     __shared__ uint32_t dmask[3];  // dirty 8x4 blocks: being swept / for the next sweep / being reset
-    __shared__ uint32_t edge_changed[4];
+    __shared__ uint32_t edge_mask;  // tile edges with a changed cell: 1 top, 2 bottom, 4 left, 8 right
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_emin[5];  // min changed value per edge [0..3], overall [4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_per_prob = p.ntx * p.nty;
+    // ---- per-thread constants of the sweep.  Warp w owns the 8x8 block(s) b = w + h * WARPS
+    // (bx = b & 3, by = b >> 2); lane (lx, ly) owns the cells (lx, ly) and (lx, ly + 4) of it,
+    // whose two update chains are independent and interleave in the in-order issue stream.
+    // wakeA / wakeB: what a change of the lane's upper / lower cell has to wake up -- the own
+    // block, the neighbour block across a block edge (bits 0..15) and the tile edge the cell
+    // sits on (bits 16..19: top, bottom, left, right).
+    // The masks live in shared memory: kept in registers the compiler re-derives them from the
+    // thread index in every sweep (64-register cap), which costs more issue slots than one load.
+    constexpr int c_off = (TILE + 1) * P - 1;  // from a cell of Ts to the same cell of Cs
+    __shared__ uint2 s_wake[K::NB][K::THREADS];
+    double* cellA[K::NB];
+    uint32_t my_bit[K::NB];
+    {
+        const int lx = lane & 7, ly = lane >> 3;
+#pragma unroll
+        for (int h = 0; h < K::NB; ++h)
+        {
+            const int b = warp + h * K::WARPS;
+            const int bx = b & 3, by = b >> 2;
+            cellA[h] = Ts + (by * 8 + ly + 1) * P + bx * 8 + lx + 1;
+            my_bit[h] = 1u << b;
+            const uint32_t bitL = bx > 0 ? my_bit[h] >> 1 : 0x40000u, bitR = bx < K::BX - 1 ? my_bit[h] << 1 : 0x80000u;
+            const uint32_t bitU = by > 0 ? my_bit[h] >> 4 : 0x10000u, bitD = by < K::BY - 1 ? my_bit[h] << 4 : 0x20000u;
+            const uint32_t side = (lx == 0 ? bitL : 0u) | (lx == 7 ? bitR : 0u);
+            s_wake[h][tid] = make_uint2(my_bit[h] | side | (ly == 0 ? bitU : 0u),
+                                        my_bit[h] | side | (ly == 3 ? bitD : 0u));
+        }
+    }
     auto sel3 = [](uint32_t* a, uint32_t* b, uint32_t* c, int k) { return k == 0 ? a : (k == 1 ? b : c); };
     auto sel3k = [](unsigned long long* a, unsigned long long* b, unsigned long long* c, int k) {
         return k == 0 ? a : (k == 1 ? b : c);
@@ -254,6 +287,11 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             if (gm != kNoKey && lim < DYMU_INF) limit = key_of(lim);
         }
 
+        // A phase lasts as long as its busiest CTA.  Every CTA therefore gets a sweep budget per
+        // phase: a tile taken late in the phase is relaxed only for what is left of it (and
+        // resumes from its saved dirty mask next phase), and once the budget is gone the CTA
+        // hands the tiles it still draws to the next phase untouched.
+        int budget = p.phase_budget;
         for (;;)
         {
             __syncthreads();
@@ -266,7 +304,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     if (idx >= n_active) break;
                     const uint32_t cand = ld_volatile_u32(&list_cur[idx]);
                     const unsigned long long k = ld_volatile_u64(&key_cur[cand]);
-                    if (k <= limit)
+                    if (k <= limit && budget >= p.min_slice)
                     {
                         t = cand;
                         break;
@@ -353,7 +391,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 flag_cur[tile_id] = 0;  // consumed; writers use flag_nxt / key_nxt this phase
                 key_cur[tile_id] = kNoKey;
             }
-            if (tid < 4) edge_changed[tid] = 0;
+            if (tid == 0) edge_mask = 0;
             if (tid < 5) s_emin[tid] = kNoKey;
             __syncthreads();
             PC_MARK(pc_load)
@@ -365,68 +403,47 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             // lane (lx, ly) owns the cells (lx, ly) and (lx, ly + 4) of it, whose two update
             // chains are independent and interleave in the in-order issue stream.  A sweep is
             // therefore one visit per warp, whatever the number of dirty blocks.
-            const int lx = lane & 7, ly = lane >> 3;
-            int oA[K::NB];
-            double cA[K::NB], cB[K::NB];
-            uint32_t my_bit[K::NB], bitL[K::NB], bitR[K::NB], bitU[K::NB], bitD[K::NB];
-#pragma unroll
-            for (int h = 0; h < K::NB; ++h)
-            {
-                const int b = warp + h * K::WARPS;
-                const int bx = b & 3, by = b >> 2;
-                oA[h] = (by * 8 + ly + 1) * P + bx * 8 + lx + 1;
-                cA[h] = Cs[(by * 8 + ly) * P + bx * 8 + lx];
-                cB[h] = Cs[(by * 8 + ly + 4) * P + bx * 8 + lx];
-                my_bit[h] = 1u << b;
-                // neighbour-block bits (0 where the block sits on the tile edge)
-                bitL[h] = bx > 0 ? my_bit[h] >> 1 : 0u;
-                bitR[h] = bx < K::BX - 1 ? my_bit[h] << 1 : 0u;
-                bitU[h] = by > 0 ? my_bit[h] >> 4 : 0u;
-                bitD[h] = by < K::BY - 1 ? my_bit[h] << 4 : 0u;
-            }
             int it = 0;
             uint32_t visits = 0;
             uint32_t* m_cur = &dmask[0];
             uint32_t* m_nxt = &dmask[1];
             uint32_t* m_old = &dmask[2];
             uint32_t m = *m_cur;
-            while (m != 0 && it < p.inner_cap)
+            const int cap = min(p.inner_cap, budget);
+            double cA[K::NB], cB[K::NB];
+#pragma unroll
+            for (int h = 0; h < K::NB; ++h)
+            {
+                cA[h] = cellA[h][c_off];
+                cB[h] = cellA[h][4 * P + c_off];
+            }
+            while (m != 0 && it < cap)
             {
                 if (tid == 0) *m_old = 0;
 #pragma unroll
                 for (int h = 0; h < K::NB; ++h)
                 {
                     if (!(m & my_bit[h])) continue;
-                    const int a = oA[h], b = a + 4 * P;
-                    const double tA = Ts[a], lA = Ts[a - 1], rA = Ts[a + 1], uA = Ts[a - P], dA = Ts[a + P];
-                    const double tB = Ts[b], lB = Ts[b - 1], rB = Ts[b + 1], uB = Ts[b - P], dB = Ts[b + P];
+                    double* a = cellA[h];
+                    double* b = a + 4 * P;
+                    const double tA = a[0], lA = a[-1], rA = a[1], uA = a[-P], dA = a[P];
+                    const double tB = b[0], lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
                     double nA, nB;
                     const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], nA);
                     const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], nB);
-                    if (chA) Ts[a] = nA;
-                    if (chB) Ts[b] = nB;
-                    const uint32_t mA = __ballot_sync(0xffffffffu, chA);
-                    const uint32_t mB = __ballot_sync(0xffffffffu, chB);
-                    const uint32_t mAB = mA | mB;
+                    if (chA) a[0] = nA;
+                    if (chB) b[0] = nB;
+                    // one warp reduction tells which blocks (bits 0..15) and which tile edges
+                    // (bits 16..19) saw a change
+                    const uint2 wake = s_wake[h][tid];
+                    const uint32_t all = __reduce_or_sync(0xffffffffu, (chA ? wake.x : 0u) | (chB ? wake.y : 0u));
                     visits += 2;
-                    if (mAB)
+                    if (all != 0 && lane == 0)
                     {
-                        uint32_t bits = my_bit[h];
-                        bits |= (mAB & kLeftLanes) ? bitL[h] : 0u;
-                        bits |= (mAB & kRightLanes) ? bitR[h] : 0u;
-                        bits |= (mA & kTopLanes) ? bitU[h] : 0u;
-                        bits |= (mB & kBottomLanes) ? bitD[h] : 0u;
-                        if (lane == 0)
-                        {
-                            atomicOr(m_nxt, bits);
-                            if (!(bitL[h] && bitR[h] && bitU[h] && bitD[h]))
-                            {
-                                if ((mAB & kLeftLanes) && !bitL[h]) edge_changed[2] = 1;
-                                if ((mAB & kRightLanes) && !bitR[h]) edge_changed[3] = 1;
-                                if ((mA & kTopLanes) && !bitU[h]) edge_changed[0] = 1;
-                                if ((mB & kBottomLanes) && !bitD[h]) edge_changed[1] = 1;
-                            }
-                        }
+                        // plain single-lane reductions (as atomicOr the compiler wraps them in
+                        // its warp-aggregation sequence)
+                        smem_or(m_nxt, all & 0xffffu);
+                        if (all >> 16) smem_or(&edge_mask, all >> 16);
                     }
                 }
                 __syncthreads();
@@ -472,10 +489,11 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             if (tid < 5)
             {
                 uint32_t target = 0xffffffffu, bit = 0;
-                if (tid == 0 && edge_changed[0] && ty > 0) { target = tile_id - p.ntx; bit = kHaloBottom; }
-                if (tid == 1 && edge_changed[1] && ty + 1 < p.nty) { target = tile_id + p.ntx; bit = kHaloTop; }
-                if (tid == 2 && edge_changed[2] && tx > 0) { target = tile_id - 1; bit = kHaloRight; }
-                if (tid == 3 && edge_changed[3] && tx + 1 < p.ntx) { target = tile_id + 1; bit = kHaloLeft; }
+                const uint32_t em = edge_mask;
+                if (tid == 0 && (em & 1u) && ty > 0) { target = tile_id - p.ntx; bit = kHaloBottom; }
+                if (tid == 1 && (em & 2u) && ty + 1 < p.nty) { target = tile_id + p.ntx; bit = kHaloTop; }
+                if (tid == 2 && (em & 4u) && tx > 0) { target = tile_id - 1; bit = kHaloRight; }
+                if (tid == 3 && (em & 8u) && tx + 1 < p.ntx) { target = tile_id + 1; bit = kHaloLeft; }
                 if (tid == 4 && more) { target = tile_id; bit = kResume; }  // cap hit: not converged
                 if (target != 0xffffffffu)
                 {
@@ -492,6 +510,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             }
             n_tiles++;
             n_inner += (unsigned long long)it;
+            budget -= it;
             PC_MARK(pc_store)
 #ifdef DYMU_FIM_PROFILE
             if (tid == 0) { GT(tl_store) tl_tiles++; }
@@ -713,6 +732,11 @@ int dymu_internal_fim_configure(dymu_ctx* ctx)
     ctx->fim_inner_cap = (int)ctx->tile * 2;
     if (const char* e = getenv("DYMU_FIM_INNER"))
         if (atoi(e) > 0) ctx->fim_inner_cap = atoi(e);
+    ctx->fim_phase_budget = 0;  // sweeps per CTA per phase; 0 = unlimited
+    if (const char* e = getenv("DYMU_FIM_BUDGET")) ctx->fim_phase_budget = atoi(e);
+    ctx->fim_min_slice = 12;
+    if (const char* e = getenv("DYMU_FIM_MIN_SLICE"))
+        if (atoi(e) > 0) ctx->fim_min_slice = atoi(e);
     ctx->fim_grid_per_sm = 0;  // 0 = as many CTAs per SM as fit
     if (const char* e = getenv("DYMU_FIM_GRID_PER_SM"))
         if (atoi(e) > 0) ctx->fim_grid_per_sm = atoi(e);
@@ -814,6 +838,8 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     prm.stats = w->stats;
     prm.band = L.band;
     prm.inner_cap = ctx->fim_inner_cap;
+    prm.phase_budget = ctx->fim_phase_budget > 0 ? ctx->fim_phase_budget : 1 << 30;
+    prm.min_slice = ctx->fim_min_slice;
     // a wave needs at most ~(ntx+nty) tile hops in free space; obstacles lengthen the
     // geodesic, so leave two orders of magnitude of head room before reporting NOCONV
     prm.max_outer = 64 * (int)(L.ntx + L.nty) + 4096;
