@@ -225,7 +225,10 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
         {
             const int b = warp + h * K::WARPS;
             const int bx = b & 3, by = b >> 2;
-            cellA[h] = Ts + (by * 8 + ly + 1) * P + bx * 8 + lx + 1;
+            // opaque offset: otherwise it is re-derived from the thread index in every sweep
+            int off = (by * 8 + ly + 1) * P + bx * 8 + lx + 1;
+            asm volatile("" : "+r"(off));
+            cellA[h] = Ts + off;
             my_bit[h] = 1u << b;
             const uint32_t bitL = bx > 0 ? my_bit[h] >> 1 : 0x40000u, bitR = bx < K::BX - 1 ? my_bit[h] << 1 : 0x80000u;
             const uint32_t bitU = by > 0 ? my_bit[h] >> 4 : 0x10000u, bitD = by < K::BY - 1 ? my_bit[h] << 4 : 0x20000u;
@@ -405,10 +408,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             // therefore one visit per warp, whatever the number of dirty blocks.
             int it = 0;
             uint32_t visits = 0;
-            uint32_t* m_cur = &dmask[0];
-            uint32_t* m_nxt = &dmask[1];
-            uint32_t* m_old = &dmask[2];
-            uint32_t m = *m_cur;
+            uint32_t m = dmask[0];
             const int cap = min(p.inner_cap, budget);
             double cA[K::NB], cB[K::NB];
 #pragma unroll
@@ -417,9 +417,10 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 cA[h] = cellA[h][c_off];
                 cB[h] = cellA[h][4 * P + c_off];
             }
-            while (m != 0 && it < cap)
-            {
-                if (tid == 0) *m_old = 0;
+            // one sweep: relax the dirty blocks listed in m, collect the next dirty set in *nxt,
+            // clear *old for the sweep after that; returns the next dirty set
+            auto sweep = [&](uint32_t* nxt, uint32_t* old) -> uint32_t {
+                if (tid == 0) *old = 0;
 #pragma unroll
                 for (int h = 0; h < K::NB; ++h)
                 {
@@ -440,19 +441,24 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     visits += 2;
                     if (all != 0 && lane == 0)
                     {
-                        // plain single-lane reductions (as atomicOr the compiler wraps them in
-                        // its warp-aggregation sequence)
-                        smem_or(m_nxt, all & 0xffffu);
+                        smem_or(nxt, all & 0xffffu);
                         if (all >> 16) smem_or(&edge_mask, all >> 16);
                     }
                 }
                 __syncthreads();
                 ++it;
-                uint32_t* t_ = m_cur;
-                m_cur = m_nxt;
-                m_nxt = m_old;
-                m_old = t_;
-                m = *m_cur;
+                return *nxt;
+            };
+            // the three mask words rotate through the roles current / next / being cleared;
+            // unrolled by three so that their addresses are constants
+            for (;;)
+            {
+                if (m == 0 || it >= cap) break;
+                m = sweep(&dmask[1], &dmask[2]);
+                if (m == 0 || it >= cap) break;
+                m = sweep(&dmask[2], &dmask[0]);
+                if (m == 0 || it >= cap) break;
+                m = sweep(&dmask[0], &dmask[1]);
             }
             n_visits += visits;
             const int more = (m != 0);
