@@ -148,29 +148,29 @@ __device__ __forceinline__ double max_nn(double a, double b)
 
 // One node update; returns true when the stored value improves.  Written branch-free so a
 // warp stays converged and two blocks can be interleaved: the two-sided (sqrt) value is
-// computed for every lane on a clamped argument and selected afterwards.  The value it
+// computed for every lane and selected afterwards.  The value it
 // produces is bit-identical to propagateGlobalNode's (G.cpp:527-535):
 //   * `Tx < inf && Ty < inf` is implied by |Tx-Ty| < C for finite C (inf-inf is NaN);
 //   * C = +inf marks cells that are never targets (obstacles, padding): no update.
 template <int MODE>
 __device__ __forceinline__ bool relax(double tc, double tl, double tr, double tu, double td,
-                                      double c, double& out)
+                                      double c, double cc2 /* 2 c^2 */, double& out)
 {
     if (MODE == 0)
     {
+        // No guards around the square root: the argument 2c^2 - d^2 lies in [c^2, 2c^2] whenever
+        // the two-sided value is selected; otherwise (one side +inf, both +inf -> d NaN, or a
+        // non-target cell with c = +inf) the root is garbage or NaN, which is either not
+        // selected or fails the final '<'.  dymu_sqrt_normal is branch-free, so junk arguments
+        // cost nothing.
         const double Tx = min_nn(tl, tr), Ty = min_nn(td, tu);
         const double d = Tx - Ty;
         const bool two = fabs(d) < c;             // false for NaN d (both inf) and for d = +-inf
-        const bool target = c < DYMU_INF;
-        double arg = (two && target) ? (2 * (c * c) - (d * d)) : 1.0;
-        // keep the select in front of the sqrt: hoisting it would feed -inf / NaN arguments
-        // into dsqrt and send the warp through the library's slow path at every wave front
-        asm volatile("" : "+d"(arg));
-        const double t2 = (Tx + Ty + dymu_sqrt_normal(arg)) / 2;  // arg in [c^2, 2c^2] or 1
+        const double t2 = (Tx + Ty + dymu_sqrt_normal(cc2 - (d * d))) * 0.5;
         const double t1 = min_nn(Tx, Ty) + c;
         const double Tn = two ? t2 : t1;
         out = Tn;
-        return target && (Tn < tc);
+        return Tn < tc;  // c = +inf (obstacle, padding): Tn is +inf or NaN, never smaller
     }
     else
     {
@@ -410,12 +410,14 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             uint32_t visits = 0;
             uint32_t m = dmask[0];
             const int cap = min(p.inner_cap, budget);
-            double cA[K::NB], cB[K::NB];
+            double cA[K::NB], cB[K::NB], qA[K::NB], qB[K::NB];
 #pragma unroll
             for (int h = 0; h < K::NB; ++h)
             {
                 cA[h] = cellA[h][c_off];
                 cB[h] = cellA[h][4 * P + c_off];
+                qA[h] = 2 * (cA[h] * cA[h]);
+                qB[h] = 2 * (cB[h] * cB[h]);
             }
             // one sweep: relax the dirty blocks listed in m, collect the next dirty set in *nxt,
             // clear *old for the sweep after that; returns the next dirty set
@@ -430,8 +432,8 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     const double tA = a[0], lA = a[-1], rA = a[1], uA = a[-P], dA = a[P];
                     const double tB = b[0], lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
                     double nA, nB;
-                    const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], nA);
-                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], nB);
+                    const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], qA[h], nA);
+                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], qB[h], nB);
                     if (chA) a[0] = nA;
                     if (chB) b[0] = nB;
                     // one warp reduction tells which blocks (bits 0..15) and which tile edges
