@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
         // resumes from its saved dirty mask next phase), and once the budget is gone the CTA
         // hands the tiles it still draws to the next phase untouched.
         int budget = p.phase_budget;
+        bool first_fetch = true;
         for (;;)
         {
             __syncthreads();
@@ -303,7 +304,16 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 uint32_t t = 0xffffffffu;
                 for (;;)
                 {
-                    const uint32_t idx = atomicAdd(&p.ctrl[3 + cur], 1u);
+                    // the first gridDim.x entries of a phase are pre-assigned, one per CTA; the
+                    // shared cursor only hands out the rest
+                    uint32_t idx;
+                    if (first_fetch)
+                    {
+                        idx = blockIdx.x;
+                        first_fetch = false;
+                    }
+                    else
+                        idx = gridDim.x + atomicAdd(&p.ctrl[3 + cur], 1u);
                     if (idx >= n_active) break;
                     const uint32_t cand = ld_volatile_u32(&list_cur[idx]);
                     const unsigned long long k = ld_volatile_u64(&key_cur[cand]);
@@ -341,6 +351,37 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 
             // ---- stage the tile: T interior + halo (L2-coherent loads: other CTAs write
             // T during this phase), C through the read-only path
+            // All global loads of a thread are issued before the first one is consumed, so that
+            // staging costs one memory round trip (the halo used to be a second one).
+            static_assert(4 * TILE <= K::THREADS, "one halo cell per thread");
+            double hv = outside_value<MODE>();
+            int hslot = -1;
+            if (tid < 4 * TILE)
+            {
+                const int side = tid / TILE, q = tid % TILE;
+                const double* src = nullptr;
+                if (side == 0)
+                {
+                    if (ty > 0) src = &Tg[-(ptrdiff_t)p.pitch + q];
+                    hslot = q + 1;
+                }
+                else if (side == 1)
+                {
+                    if (ty + 1 < p.nty) src = &Tg[(size_t)TILE * p.pitch + q];
+                    hslot = (TILE + 1) * P + q + 1;
+                }
+                else if (side == 2)
+                {
+                    if (tx > 0) src = &Tg[(size_t)q * p.pitch - 1];
+                    hslot = (q + 1) * P;
+                }
+                else
+                {
+                    if (tx + 1 < p.ntx) src = &Tg[(size_t)q * p.pitch + TILE];
+                    hslot = (q + 1) * P + TILE + 1;
+                }
+                if (src) hv = __ldcg(src);
+            }
             double told[K::CPT];
 #pragma unroll
             for (int k = 0; k < K::CPT; ++k)
@@ -352,31 +393,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 Ts[(y + 1) * P + x + 1] = v;
                 Cs[y * P + x] = __ldg(&Cg[(size_t)y * p.pitch + x]);
             }
-            for (int e = tid; e < 4 * TILE; e += K::THREADS)
-            {
-                int side = e / TILE, q = e % TILE;
-                double v = outside_value<MODE>();
-                if (side == 0)
-                {
-                    if (ty > 0) v = __ldcg(&Tg[-(ptrdiff_t)p.pitch + q]);
-                    Ts[q + 1] = v;
-                }
-                else if (side == 1)
-                {
-                    if (ty + 1 < p.nty) v = __ldcg(&Tg[(size_t)TILE * p.pitch + q]);
-                    Ts[(TILE + 1) * P + q + 1] = v;
-                }
-                else if (side == 2)
-                {
-                    if (tx > 0) v = __ldcg(&Tg[(size_t)q * p.pitch - 1]);
-                    Ts[(q + 1) * P] = v;
-                }
-                else
-                {
-                    if (tx + 1 < p.ntx) v = __ldcg(&Tg[(size_t)q * p.pitch + TILE]);
-                    Ts[(q + 1) * P + TILE + 1] = v;
-                }
-            }
+            if (hslot >= 0) Ts[hslot] = hv;
             // initial dirty set: the blocks along the stale halos (+ what an interrupted
             // sweep left over), or everything for a seeded tile
             if (tid == 0)
@@ -492,7 +509,10 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     }
                 }
             }
-            __threadfence();
+            // No fence here: the values and the wake-ups are consumed after the grid barrier,
+            // whose arrival (bar.sync, then thread 0's cumulative fence) orders them; tiles that
+            // read this one's cells during the same phase may see old or new values, both are
+            // valid upper bounds.
             __syncthreads();
             if (tid < 5)
             {
