@@ -20,13 +20,25 @@
 //     T back and, for every tile edge whose cells changed, appends the neighbouring tile
 //     to the next list (deduplicated by an atomic flag word whose bits say WHICH halo of
 //     the neighbour went stale);
-//   * inside a tile, work is tracked per 8x4-cell warp block: a warp only re-evaluates
-//     blocks marked dirty (a neighbouring cell changed in the previous sweep), found with
-//     __ballot_sync on the per-lane "improved" predicate; __syncthreads_or detects tile
-//     convergence.  A wave crossing a tile therefore costs work proportional to the
-//     front length, not the tile area;
+//   * inside a tile, work is tracked per 8x8-cell block, one block per warp (two cells per
+//     lane): a warp only re-evaluates its block if it is marked dirty (a cell of it or of the
+//     facing edge of a neighbouring block changed in the previous sweep).  One warp-wide OR
+//     (REDUX) of per-lane wake masks tells which blocks and tile edges a sweep touched; the
+//     16-bit dirty masks rotate through three shared words, one __syncthreads per sweep.  A
+//     wave crossing a tile therefore costs work proportional to the front length, not the
+//     tile area;
+//   * every wake-up carries the smallest changed value as a priority key; a phase only
+//     relaxes the tiles whose key lies within a band above the smallest pending key, the
+//     others are carried over untouched (far fewer sweeps with halos that are not final yet);
 //   * phases are separated by a grid-wide barrier; three rotating lists let one be
-//     reset while the next is filled.
+//     reset while the next is filled;
+//   * a solve can be stopped after a bounded number of phases and continued later
+//     (dymu_solve_start / dymu_solve_advance): the lists stay consistent at phase boundaries.
+// Environment switches (read once per context): DYMU_FIM_BAND (band width factor, default
+// 4), DYMU_FIM_INNER (sweep cap per activation, default 64), DYMU_FIM_BUDGET /
+// DYMU_FIM_MIN_SLICE (per-CTA sweep budget per phase, default off), DYMU_FIM_GRID_PER_SM,
+// DYMU_FIM_MAX_OUTER, DYMU_FIM_TRACE (per-phase timeline); build-time: -DDYMU_FIM_PROFILE
+// (clock64 section profile + DYMU_FIM_CTA_TRACE), -DDYMU_FIM_WARPS=8.
 // The same kernel runs the local layer's risk dilation (propagateRisk,
 // src/DyMu_LocalPathRepairing.cpp:550-576) in MODE 1, a max-propagation on risk.
 #include <cooperative_groups.h>
