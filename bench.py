@@ -355,8 +355,9 @@ def run_b200(args):
     t_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
 
     def plan_e2e():
-        dev.set_cost_map(cost_host.numpy())
-        dev.solve_total_cost([goal])
+        # setCostMap + computeEntireTotalCostMap from the pinned host buffer; the upload of the
+        # rows away from the goal runs on the copy stream behind the first solver phases
+        dev.plan_streamed(cost_host.numpy(), goal)
         # getTotalCostMatrix read-back runs on the copy stream while the path is extracted
         dev.download_total_cost_begin(t_host.numpy(), xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
         dev.extract_global_path(float(start[0]), float(start[1]), 0.4, goal[0], goal[1])

@@ -161,6 +161,14 @@ int dymu_solve_start(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t m
                      dymu_solve_stats* stats);
 int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, double seed_key,
                        uint32_t max_phases, dymu_solve_stats* stats);
+/* setCostMap (G.cpp:109-126) + computeEntireTotalCostMap (G.cpp:443-468) for a cost map that is
+ * still in host memory, with the upload hidden behind the solve: the rows around the goal go
+ * first, the solve starts on them with everything else impassable (C_eff = +inf), and after
+ * `first_phases` solver phases (0 = default) the remaining rows -- uploaded meanwhile on the copy
+ * stream -- are opened and the tiles along the two seams re-activated.  Same fixed point as
+ * dymu_set_cost_map + dymu_solve_total_cost.  `cost_host` should be pinned memory. */
+int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t goal_i,
+                       uint32_t goal_j, uint32_t first_phases, dymu_solve_stats* stats);
 /* resetTotalCostMap (G.cpp:473-485) without seeding a goal: every slot-0 value = +inf. */
 int dymu_reset_total_cost(dymu_ctx* ctx);
 /* Halo exchange for row-strip domain decomposition.  Rows are dense (nx doubles each).

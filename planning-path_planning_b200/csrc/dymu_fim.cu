@@ -1146,6 +1146,82 @@ int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges,
     return solve_resume_impl(ctx, ranges, n_ranges, true, seed_key, max_phases, stats);
 }
 
+int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t goal_i, uint32_t goal_j,
+                       uint32_t first_phases, dymu_solve_stats* stats)
+{
+    if (!ctx || !cost_host || ld < ctx->nx || goal_i >= ctx->nx || goal_j >= ctx->ny) return DYMU_ERR_ARG;
+    if (first_phases == 0) first_phases = 40;
+    const uint32_t tile = ctx->tile, ny = ctx->ny;
+    // part A: the rows around the goal, uploaded first; part B: everything else
+    uint32_t reach = ny / 8 < 256 ? 256 : ny / 8;
+    uint32_t a0 = goal_j > reach ? ((goal_j - reach) / tile) * tile : 0;
+    uint32_t a1 = goal_j + reach < ny ? dymu_div_up(goal_j + reach, tile) * tile : ny;
+    if (a1 > ny) a1 = ny;
+    auto h2d_rows = [&](uint32_t j0, uint32_t j1) -> int {
+        if (j0 >= j1) return DYMU_OK;
+        DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->cost + (size_t)j0 * ctx->pitch, ctx->pitch * sizeof(double),
+                                             cost_host + (size_t)j0 * ld, ld * sizeof(double),
+                                             ctx->nx * sizeof(double), j1 - j0, cudaMemcpyHostToDevice,
+                                             ctx->copy_stream));
+        return DYMU_OK;
+    };
+    // the copies must not overtake earlier work on the planes (a previous plan's read-back)
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    DYMU_TRY(h2d_rows(a0, a1));
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_part, ctx->copy_stream));
+    DYMU_TRY(h2d_rows(0, a0));
+    DYMU_TRY(h2d_rows(a1, ny));
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    // everything not uploaded yet is impassable for now
+    DYMU_TRY(dymu_internal_fill(ctx, ctx->ceff, 1.0 / 0.0, (size_t)ctx->pitch * ctx->rows));
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_part, 0));
+    DYMU_TRY(dymu_internal_cost_rows(ctx, a0, a1));
+    ctx->have_cost = true;
+    ctx->ceff_dirty = false;
+    if (!(ctx->fim_band < 1.0 / 0.0)) DYMU_TRY(dymu_internal_band_from_rows(ctx, a0, a1));
+    dymu_solve_stats first, rest;
+    memset(&first, 0, sizeof(first));
+    memset(&rest, 0, sizeof(rest));
+    DYMU_TRY(solve_total_cost_impl(ctx, 1, &goal_i, &goal_j, first_phases, &first));
+    // the rest has arrived meanwhile: open it up and wake the tiles along the two seams
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    uint32_t ranges[4];
+    uint32_t n_ranges = 0;
+    if (a0 > 0)
+    {
+        DYMU_TRY(dymu_internal_cost_rows(ctx, 0, a0));
+        ranges[2 * n_ranges] = a0 - 1;
+        ranges[2 * n_ranges + 1] = a0 + 1;
+        n_ranges++;
+    }
+    if (a1 < ny)
+    {
+        DYMU_TRY(dymu_internal_cost_rows(ctx, a1, ny));
+        ranges[2 * n_ranges] = a1 - 1;
+        ranges[2 * n_ranges + 1] = a1 + 1;
+        n_ranges++;
+    }
+    int rc = DYMU_OK;
+    if (n_ranges || !first.converged)
+        rc = solve_resume_impl(ctx, ranges, n_ranges, true, 0.0, 0, &rest);
+    else
+        rest.converged = 1;
+    if (stats)
+    {
+        *stats = first;
+        stats->outer_iterations += rest.outer_iterations;
+        stats->converged = rest.converged;
+        stats->tile_activations += rest.tile_activations;
+        stats->cell_updates += rest.cell_updates;
+        stats->tiles_deferred += rest.tiles_deferred;
+        stats->inner_iterations += rest.inner_iterations;
+        stats->kernel_ms += rest.kernel_ms;
+    }
+    ctx->solved = (rc == DYMU_OK);
+    return rc;
+}
+
 int dymu_reset_total_cost(dymu_ctx* ctx)
 {
     if (!ctx) return DYMU_ERR_ARG;

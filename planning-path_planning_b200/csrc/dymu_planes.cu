@@ -395,6 +395,7 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
     DYMU_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DYMU_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_part, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev2));
@@ -441,6 +442,7 @@ int dymu_destroy(dymu_ctx* ctx)
     for (int k = 0; k < 8; ++k)
         if (ctx->user_ev[k]) cudaEventDestroy(ctx->user_ev[k]);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
@@ -841,6 +843,42 @@ int dymu_count_leq(dymu_ctx* ctx, uint32_t slot, double threshold, uint64_t* n_f
 }
 
 }  // extern "C"
+
+int dymu_internal_cost_rows(dymu_ctx* ctx, uint32_t j0, uint32_t j1)
+{
+    if (j0 >= j1 || j1 > ctx->ny) return DYMU_ERR_ARG;
+    const size_t off = (size_t)j0 * ctx->pitch;
+    const uint32_t nr = j1 - j0;
+    const size_t n = (size_t)ctx->pitch * nr;
+    k_set_cost_map<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(
+        ctx->cost + off, ctx->obst + off, ctx->traff + off, ctx->haz + off, ctx->pitch, ctx->nx, nr);
+    ctx->launches++;
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    k_ceff<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->cost + off, ctx->haz + off, ctx->traff + off,
+                                                             ctx->obst + off, ctx->ceff + off, ctx->gres,
+                                                             ctx->pitch, nr, ctx->nx, nr);
+    ctx->launches++;
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    return DYMU_OK;
+}
+
+int dymu_internal_band_from_rows(dymu_ctx* ctx, uint32_t j0, uint32_t j1)
+{
+    ctx->fim_band = 1.0 / 0.0;
+    if (!(ctx->fim_band_factor > 0) || j0 >= j1 || j1 > ctx->rows) return DYMU_OK;
+    const size_t n = (size_t)ctx->pitch * (j1 - j0);
+    DYMU_TRY(dymu_internal_scratch(ctx, 64, 64));
+    double* d = (double*)ctx->d_scratch;
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    k_ceff_stats<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->ceff + (size_t)j0 * ctx->pitch, n, d);
+    ctx->launches++;
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    double h[2] = {0, 0};
+    DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[1] > 0) ctx->fim_band = ctx->fim_band_factor * (double)ctx->tile * (h[0] / h[1]);
+    return DYMU_OK;
+}
 
 int dymu_internal_refresh_ceff(dymu_ctx* ctx)
 {

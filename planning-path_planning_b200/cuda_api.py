@@ -68,6 +68,8 @@ _SIG = {
     "dymu_solve_start": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(SolveStats)]),
     "dymu_solve_advance": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, C.c_double, C.c_uint32,
                                      C.POINTER(SolveStats)]),
+    "dymu_plan_streamed": (C.c_int, [C.c_void_p, _dp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.POINTER(SolveStats)]),
     "dymu_reset_total_cost": (C.c_int, [C.c_void_p]),
     "dymu_export_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]),
     "dymu_import_rows_min": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -293,6 +295,14 @@ class DeviceLayer:
         st = SolveStats()
         self._chk(self._l.dymu_solve_advance(self._h, r.ctypes.data_as(_u32p), r.shape[0], float(seed_key),
                                              int(max_phases), C.byref(st)))
+        return st.as_dict()
+
+    def plan_streamed(self, cost_host, goal, first_phases=0):
+        """set_cost_map(cost_host) + solve_total_cost([goal]) with the upload overlapped with the
+        solve (cost_host: C-contiguous float64 [ny, nx], pinned for a truly asynchronous copy)."""
+        st = SolveStats()
+        self._chk(self._l.dymu_plan_streamed(self._h, cost_host.ctypes.data_as(_dp), cost_host.shape[1],
+                                             int(goal[0]), int(goal[1]), int(first_phases), C.byref(st)))
         return st.as_dict()
 
     def reset_total_cost(self):

@@ -129,3 +129,28 @@ def test_overlapped_total_cost_download(pkg):
     # and the context keeps working afterwards
     dev.solve_total_cost([goal])
     assert np.array_equal(dev.download_total_cost(xform=pkg.cuda_api.XFORM_INF_TO_MINUS1), want)
+
+
+@pytest.mark.parametrize("goal_xy,first_phases", [((150, 300), 3), ((40, 20), 1), ((200, 590), 50)])
+def test_streamed_plan_equals_upload_then_solve(pkg, goal_xy, first_phases):
+    """dymu_plan_streamed (rows around the goal first, the rest opened while the solve is under
+    way) reaches the fixed point of dymu_set_cost_map + dymu_solve_total_cost, twice in a row on
+    different maps (the second call must not see anything of the first)."""
+    nx, ny = 352, 608
+    api, syn = pkg.cuda_api, pkg.synthetic
+    for seed in (31, 32):
+        cost = syn.smooth_cost_map(ny, nx, seed=seed, obstacle_fraction=0.0)
+        plain = api.DeviceLayer(nx, ny)
+        plain.set_cost_map(cost)
+        goal = syn.free_interior_cell_near(plain.download_plane_u8("obstacle"), *goal_xy)
+        plain.solve_total_cost([goal])
+        want = plain.download_total_cost()
+        if seed == 31:
+            dev = api.DeviceLayer(nx, ny)
+        st = dev.plan_streamed(np.ascontiguousarray(cost), goal, first_phases)
+        assert st["converged"]
+        got = dev.download_total_cost()
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+        fin = np.isfinite(want) & (want > 0)
+        assert np.max(np.abs(got[fin] - want[fin]) / want[fin]) <= 1e-13
+        assert np.array_equal(dev.download_plane("ceff"), plain.download_plane("ceff"))
