@@ -458,8 +458,16 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     if (!(m & my_bit[h])) continue;
                     double* a = cellA[h];
                     double* b = a + 4 * P;
-                    const double tA = a[0], lA = a[-1], rA = a[1], uA = a[-P], dA = a[P];
-                    const double tB = b[0], lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
+                    // requested with the cell values and pinned here: left to the compiler the
+                    // load sinks below the update and its latency lands on the chain
+                    uint2 wake = s_wake[h][tid];
+                    asm volatile("" : "+r"(wake.x), "+r"(wake.y));
+                    double tA = a[0];
+                    const double lA = a[-1], rA = a[1], uA = a[-P], dA = a[P];
+                    asm volatile("" : "+d"(tA));
+                    double tB = b[0];
+                    const double lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
+                    asm volatile("" : "+d"(tB));  // keep the two "current value" loads up here too
                     double nA, nB;
                     const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], qA[h], nA);
                     const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], qB[h], nB);
@@ -467,7 +475,6 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     if (chB) b[0] = nB;
                     // one warp reduction tells which blocks (bits 0..15) and which tile edges
                     // (bits 16..19) saw a change
-                    const uint2 wake = s_wake[h][tid];
                     const uint32_t all = __reduce_or_sync(0xffffffffu, (chA ? wake.x : 0u) | (chB ? wake.y : 0u));
                     visits += 2;
                     if (all != 0 && lane == 0)
