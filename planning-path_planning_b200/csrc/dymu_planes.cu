@@ -195,16 +195,38 @@ __global__ void k_smooth_cost(const double* __restrict__ raw, double* __restrict
 __global__ void k_ceff(const double* __restrict__ cost, const double* __restrict__ haz,
                        const double* __restrict__ traff, const uint8_t* __restrict__ obst,
                        double* __restrict__ ceff, double gres, uint32_t pitch, uint32_t rows,
-                       uint32_t nx, uint32_t ny)
+                       uint32_t nx, uint32_t ny, double* stats)
 {
     size_t total = (size_t)pitch * rows;
     size_t stride = (size_t)gridDim.x * blockDim.x;
+    double sum = 0, cnt = 0;  // of the finite values: sets the width of the solver's priority band
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride)
     {
         uint32_t j = (uint32_t)(q / pitch), i = (uint32_t)(q % pitch);
         double c = DYMU_INF;
-        if (i < nx && j < ny && !obst[q]) c = gres * (cost[q]) * (2 + haz[q] - traff[q]);
+        if (i < nx && j < ny && !obst[q])
+        {
+            c = gres * (cost[q]) * (2 + haz[q] - traff[q]);
+            if (c < DYMU_INF)
+            {
+                sum += c;
+                cnt += 1.0;
+            }
+        }
         ceff[q] = c;
+    }
+    if (stats)
+    {
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            sum += __shfl_down_sync(0xffffffffu, sum, o);
+            cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        }
+        if ((threadIdx.x & 31) == 0 && cnt > 0)
+        {
+            atomicAdd(&stats[0], sum);
+            atomicAdd(&stats[1], cnt);
+        }
     }
 }
 
@@ -759,7 +781,7 @@ int dymu_time_stencils(dymu_ctx* ctx, float ms[6])
         DYMU_CUDA_TRY(ctx, tick(ctx->ev0));
         k_ceff<<<stream_grid(ctx, np), kThreads, 0, ctx->stream>>>(ctx->cost, ctx->haz, ctx->traff, ctx->obst,
                                                                 ctx->ceff, ctx->gres, ctx->pitch, ctx->rows,
-                                                                ctx->nx, ctx->ny);
+                                                                ctx->nx, ctx->ny, nullptr);
         DYMU_TRY(lap(1));
         DYMU_CUDA_TRY(ctx, tick(ctx->ev0));
         k_readback<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->T, ctx->haz, ctx->traff, ctx->obst,
@@ -856,7 +878,7 @@ int dymu_internal_cost_rows(dymu_ctx* ctx, uint32_t j0, uint32_t j1)
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     k_ceff<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->cost + off, ctx->haz + off, ctx->traff + off,
                                                              ctx->obst + off, ctx->ceff + off, ctx->gres,
-                                                             ctx->pitch, nr, ctx->nx, nr);
+                                                             ctx->pitch, nr, ctx->nx, nr, nullptr);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     return DYMU_OK;
@@ -884,21 +906,25 @@ int dymu_internal_refresh_ceff(dymu_ctx* ctx)
 {
     if (!ctx->ceff_dirty) return DYMU_OK;
     size_t n = (size_t)ctx->pitch * ctx->rows;
+    // the same pass accumulates sum and count of the finite values: the band width of the tile
+    // scheduler is a few tile crossings worth of total cost
+    const bool want_band = ctx->fim_band_factor > 0;
+    double* d = nullptr;
+    if (want_band)
+    {
+        DYMU_TRY(dymu_internal_scratch(ctx, 64, 64));
+        d = (double*)ctx->d_scratch;
+        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    }
     k_ceff<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->cost, ctx->haz, ctx->traff,
                                                              ctx->obst, ctx->ceff, ctx->gres,
                                                              ctx->pitch, ctx->rows, ctx->nx,
-                                                             ctx->ny);
+                                                             ctx->ny, d);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
-    // band width of the tile scheduler: a few tile crossings worth of total cost
     ctx->fim_band = 1.0 / 0.0;
-    if (ctx->fim_band_factor > 0)
+    if (want_band)
     {
-        double* d = (double*)ctx->d_scratch;
-        DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
-        k_ceff_stats<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(ctx->ceff, n, d);
-        ctx->launches++;
-        DYMU_CUDA_TRY(ctx, cudaGetLastError());
         double h[2] = {0, 0};
         DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
         DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
