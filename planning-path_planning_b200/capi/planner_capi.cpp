@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -37,17 +38,35 @@ namespace
 {
 // The reference prints progress to std::cout inside the local layer
 // (L.cpp:280,584-585,602-608,641-643,680-682).  Silence it unless asked.
+// Process-wide and reference-counted: planners may be driven from several threads at once
+// (bench.py --impl reference), and swapping std::cout's buffer per call would let one thread
+// restore another thread's already destroyed sink.
+struct NullBuf : std::streambuf
+{
+    int overflow(int c) override { return c; }
+};
+std::mutex g_quiet_mutex;
+int g_quiet_depth = 0;
+std::streambuf* g_quiet_saved = nullptr;
+NullBuf* null_buf()
+{
+    static NullBuf* b = new NullBuf;  // never destroyed: std::cout may outlive every static here
+    return b;
+}
 struct CoutSilencer
 {
-    std::streambuf* saved;
-    std::ostringstream sink;
-    CoutSilencer() : saved(nullptr)
+    bool active;
+    CoutSilencer() : active(!std::getenv("DYMU_CAPI_VERBOSE"))
     {
-        if (!std::getenv("DYMU_CAPI_VERBOSE")) saved = std::cout.rdbuf(sink.rdbuf());
+        if (!active) return;
+        std::lock_guard<std::mutex> guard(g_quiet_mutex);
+        if (g_quiet_depth++ == 0) g_quiet_saved = std::cout.rdbuf(null_buf());
     }
     ~CoutSilencer()
     {
-        if (saved) std::cout.rdbuf(saved);
+        if (!active) return;
+        std::lock_guard<std::mutex> guard(g_quiet_mutex);
+        if (--g_quiet_depth == 0) std::cout.rdbuf(g_quiet_saved);
     }
 };
 
