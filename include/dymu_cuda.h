@@ -70,6 +70,9 @@ typedef struct dymu_solve_stats
     uint64_t inner_iterations;  /* shared-memory sweeps summed over tile activations */
     float kernel_ms;            /* device time of the solve kernel(s), CUDA events */
     float reset_ms;             /* device time of the total-cost reset */
+    uint32_t goal_obstacle;     /* goals that sit on an obstacle cell and were therefore not seeded
+                                   ("The goal is not valid", G.cpp:370-374) */
+    uint32_t reserved_;
 } dymu_solve_stats;
 
 /* ---- context ---------------------------------------------------------- */
@@ -161,6 +164,13 @@ int dymu_solve_start(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t m
                      dymu_solve_stats* stats);
 int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, double seed_key,
                        uint32_t max_phases, dymu_solve_stats* stats);
+/* setCostMap (G.cpp:109-126) without waiting for the copy: the rows around `first_row` (the
+ * goal's row; >= ny = middle) are sent first on the copy stream, and the call returns at once.  The
+ * next dymu_solve_total_cost with a single goal inside those first rows starts on them while the
+ * rest is still arriving (see dymu_plan_streamed); every other entry point first completes the
+ * upload and the obstacle bookkeeping, exactly as dymu_set_cost_map would have.  `cost_host` must
+ * stay valid and unchanged until that next call returns, and should be pinned memory. */
+int dymu_set_cost_map_begin(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t first_row);
 /* setCostMap (G.cpp:109-126) + computeEntireTotalCostMap (G.cpp:443-468) for a cost map that is
  * still in host memory, with the upload hidden behind the solve: the rows around the goal go
  * first, the solve starts on them with everything else impassable (C_eff = +inf), and after

@@ -132,6 +132,18 @@ int dymu_planner_recompute_cost_map(dymu_planner* p);
 
 /* seconds spent inside the last call of the given kind (wrapper-side
  * steady_clock around the forwarded method; conversions excluded) */
+/* Copy-free variants (extensions of the B200 drop-in; the reference build implements them on top
+ * of the by-value methods so that the same call sequence runs on both):
+ *   set_cost_map_flat          setCostMap(const double*, ld) -- with a goal in place the upload is
+ *                              streamed behind the next computeEntireTotalCostMap; the buffer must
+ *                              stay unchanged until that call returns
+ *   set_total_cost_target      setTotalCostMatrixTarget(out, ld): deliver the total-cost matrix
+ *                              into `out` right after every solve
+ *   get_total_cost_matrix_flat getTotalCostMatrix(out, ld) */
+int dymu_planner_set_cost_map_flat(dymu_planner* p, const double* cost, unsigned ld);
+int dymu_planner_set_total_cost_target(dymu_planner* p, double* out, unsigned ld);
+int dymu_planner_get_total_cost_matrix_flat(dymu_planner* p, double* out, unsigned ld);
+
 double dymu_planner_last_call_seconds(dymu_planner* p);
 
 #ifdef __cplusplus

@@ -406,6 +406,46 @@ int dymu_planner_get_node_field(dymu_planner* p, int field, double* out)
 #endif
 }
 
+int dymu_planner_set_cost_map_flat(dymu_planner* p, const double* cost, unsigned ld)
+{
+    if (!p || !cost || ld < p->nx) return -1;
+#if defined(DYMU_CAPI_B200)
+    Stopwatch sw(&p->last_seconds);
+    return p->impl->setCostMap(cost, (size_t)ld) ? 1 : 0;
+#else
+    std::vector<std::vector<double>> m(p->ny);
+    for (unsigned j = 0; j < p->ny; ++j) m[j].assign(cost + (size_t)j * ld, cost + (size_t)j * ld + p->nx);
+    Stopwatch sw(&p->last_seconds);
+    return p->impl->setCostMap(m) ? 1 : 0;
+#endif
+}
+
+int dymu_planner_set_total_cost_target(dymu_planner* p, double* out, unsigned ld)
+{
+    if (!p || (out && ld < p->nx)) return -1;
+#if defined(DYMU_CAPI_B200)
+    p->impl->setTotalCostMatrixTarget(out, (size_t)ld);
+#endif
+    return 1;  // the reference has nothing to prepare
+}
+
+int dymu_planner_get_total_cost_matrix_flat(dymu_planner* p, double* out, unsigned ld)
+{
+    if (!p || !out || ld < p->nx) return -1;
+#if defined(DYMU_CAPI_B200)
+    Stopwatch sw(&p->last_seconds);
+    return p->impl->getTotalCostMatrix(out, (size_t)ld) ? 1 : 0;
+#else
+    std::vector<std::vector<double>> m;
+    {
+        Stopwatch sw(&p->last_seconds);
+        m = p->impl->getTotalCostMatrix();
+    }
+    for (unsigned j = 0; j < p->ny; ++j) std::memcpy(out + (size_t)j * ld, m[j].data(), sizeof(double) * p->nx);
+    return 1;
+#endif
+}
+
 double dymu_planner_last_call_seconds(dymu_planner* p) { return p ? p->last_seconds : 0.0; }
 
 }  // extern "C"

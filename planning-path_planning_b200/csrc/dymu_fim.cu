@@ -203,6 +203,7 @@ __device__ __forceinline__ bool relax(double tc, double tl, double tr, double tu
     }
 }
 
+
 template <int TILE, int MODE>
 __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim(Params p)
 {
@@ -608,24 +609,32 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     }
 }
 
+
+// One thread seeds all goals (there are at most a few hundred).  A goal on an obstacle cell is not
+// seeded and counted in stats[15]: "The goal is not valid", G.cpp:370-374 / 447-451.
 __global__ void k_seed(double* T, size_t slot_stride, uint32_t pitch, uint32_t ntx, uint32_t nty,
-                       int tile, const uint32_t* goal_ij, uint32_t n, uint32_t* list0,
+                       int tile, const uint32_t* goal_ij, uint32_t n, const uint8_t* obst, uint32_t* list0,
                        uint32_t* flag0, unsigned long long* key0, unsigned long long* gmin,
-                       uint32_t* ctrl)
+                       uint32_t* ctrl, unsigned long long* stats)
 {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    uint32_t gi = goal_ij[2 * q], gj = goal_ij[2 * q + 1];
-    T[(size_t)q * slot_stride + (size_t)gj * pitch + gi] = 0.0;  // resetGlobalNarrowBand, G.cpp:490-496
-    uint32_t tile_id = q * ntx * nty + (gj / tile) * ntx + gi / tile;
-    flag0[tile_id] = kFull;
-    key0[tile_id] = 0ull;
-    list0[q] = tile_id;
-    if (q == 0)
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t n_seeded = 0;
+    for (uint32_t q = 0; q < n; ++q)
     {
-        ctrl[0] = n;
-        gmin[0] = 0ull;
+        uint32_t gi = goal_ij[2 * q], gj = goal_ij[2 * q + 1];
+        if (obst && obst[(size_t)gj * pitch + gi])
+        {
+            stats[15]++;
+            continue;
+        }
+        T[(size_t)q * slot_stride + (size_t)gj * pitch + gi] = 0.0;  // resetGlobalNarrowBand, G.cpp:490-496
+        uint32_t tile_id = q * ntx * nty + (gj / tile) * ntx + gi / tile;
+        flag0[tile_id] = kFull;
+        key0[tile_id] = 0ull;
+        list0[n_seeded++] = tile_id;
     }
+    ctrl[0] = n_seeded;
+    if (n_seeded) gmin[0] = 0ull;
 }
 
 __global__ void k_seed_all(uint32_t n, uint32_t* list0, uint32_t* flag0, unsigned long long* key0,
@@ -747,6 +756,9 @@ int dymu_internal_fim_alloc(dymu_ctx* ctx, dymu_fim_work* w, size_t capacity)
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->dsave, capacity * sizeof(uint32_t)));
     DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w->dsave, 0, capacity * sizeof(uint32_t), ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&w->stats, 16 * sizeof(unsigned long long)));
+    w->rot = 0;
+    w->pending = false;
+    w->unclean = false;
     return DYMU_OK;
 }
 
@@ -821,12 +833,26 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     else
     {
         dymu_fim_work* w0 = L.work;
+        if (w0->unclean)
+        {
+            // the previous launch did not drain its lists (phase-bounded solve that was abandoned,
+            // NOCONV, failed launch): wake-up flags, keys and saved dirty masks may be set, and a set
+            // flag would swallow the wake-up of that tile in this solve
+            for (int k = 0; k < 3; ++k)
+            {
+                DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w0->flag[k], 0, w0->capacity * sizeof(uint32_t), ctx->stream));
+                DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w0->key[k], 0xFF, w0->capacity * sizeof(unsigned long long),
+                                                   ctx->stream));
+            }
+            DYMU_CUDA_TRY(ctx, cudaMemsetAsync(w0->dsave, 0, w0->capacity * sizeof(uint32_t), ctx->stream));
+        }
         DYMU_TRY(dymu_internal_fim_reset(ctx, w0));
         w0->rot = 0;
+        w0->pending = false;
         if (L.seed_kind == 0)
-            k_seed<<<dymu_div_up(L.n_initial, 128), 128, 0, ctx->stream>>>(
-                L.T, L.slot_stride, L.pitch, L.ntx, L.nty, L.tile, L.seed_data, L.n_initial, w0->list[0],
-                w0->flag[0], w0->key[0], w0->gmin, w0->ctrl);
+            k_seed<<<1, 32, 0, ctx->stream>>>(L.T, L.slot_stride, L.pitch, L.ntx, L.nty, L.tile, L.seed_data,
+                                              L.n_initial, L.goal_obst, w0->list[0], w0->flag[0], w0->key[0],
+                                              w0->gmin, w0->ctrl, w0->stats);
         else if (L.seed_kind == 1)
         {
             if (L.n_initial)
@@ -895,6 +921,7 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     if (L.max_phases > 0) prm.max_outer = (int)L.max_phases;
     prm.outer0 = w->rot;
     size_t total_tiles = (size_t)L.ntx * L.nty * L.nprob;
+    w->unclean = true;  // until this launch reports that it drained its lists
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     int rc;
     rc = (L.mode == 0) ? launch_fim<32, 0>(ctx, prm, total_tiles) : launch_fim<32, 1>(ctx, prm, total_tiles);
@@ -948,10 +975,12 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
         stats->converged = (uint32_t)h[3];
         stats->tiles_deferred = h[4];
         stats->inner_iterations = h[5];
+        stats->goal_obstacle = (uint32_t)h[15];
         DYMU_CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev1, ctx->ev2));
     }
     w->rot = (int)((prm.outer0 + h[2]) % 3);
     w->pending = !h[3];
+    w->unclean = !h[3];
     if (!h[3] && L.max_phases == 0)
         DYMU_FAIL(ctx, DYMU_ERR_NOCONV, "tile FIM hit the outer-iteration cap (%d) before converging",
                   prm.max_outer);
@@ -998,6 +1027,7 @@ extern "C" {
 
 int dymu_selftest_sqrt(dymu_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches, double* first_bad)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !mismatches) return DYMU_ERR_ARG;
     unsigned long long* d = (unsigned long long*)ctx->d_scratch;
     DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
@@ -1014,6 +1044,7 @@ int dymu_selftest_sqrt(dymu_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* misma
 
 int dymu_reserve_slots(dymu_ctx* ctx, uint32_t n_slots)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || n_slots < 1) return DYMU_ERR_ARG;
     if (n_slots == ctx->n_slots) return DYMU_OK;
     size_t n = (size_t)ctx->pitch * ctx->rows;
@@ -1055,6 +1086,7 @@ static int solve_total_cost_impl(dymu_ctx* ctx, uint32_t n_goals, const uint32_t
     L.ntx = ctx->ntx; L.nty = ctx->nty; L.nprob = n_goals; L.mode = 0; L.tile = (int)ctx->tile;
     L.work = &ctx->work; L.n_initial = n_goals; L.band = ctx->fim_band;
     L.seed_kind = 0; L.seed_data = (const uint32_t*)ctx->d_scratch;
+    L.goal_obst = ctx->obst;
     L.max_phases = max_phases;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
@@ -1068,15 +1100,28 @@ static int solve_total_cost_impl(dymu_ctx* ctx, uint32_t n_goals, const uint32_t
     return rc;
 }
 
+static int solve_streamed(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t first_phases,
+                          dymu_solve_stats* stats);
+
 int dymu_solve_total_cost(dymu_ctx* ctx, uint32_t n_goals, const uint32_t* goal_i,
                           const uint32_t* goal_j, dymu_solve_stats* stats)
 {
+    DYMU_GUARD_ONLY(ctx);
+    if (ctx && ctx->upload_pending)
+    {
+        // a cost map is still on its way (dymu_set_cost_map_begin): start on the rows that are there
+        if (n_goals == 1 && goal_i && goal_j && goal_i[0] < ctx->nx && goal_j[0] >= ctx->up_a0
+            && goal_j[0] < ctx->up_a1)
+            return solve_streamed(ctx, goal_i[0], goal_j[0], 0, stats);
+        DYMU_TRY(dymu_internal_settle_upload(ctx));
+    }
     return solve_total_cost_impl(ctx, n_goals, goal_i, goal_j, 0, stats);
 }
 
 int dymu_solve_start(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t max_phases,
                      dymu_solve_stats* stats)
 {
+    DYMU_GUARD(ctx);
     if (max_phases == 0) return DYMU_ERR_ARG;
     return solve_total_cost_impl(ctx, 1, &goal_i, &goal_j, max_phases, stats);
 }
@@ -1142,6 +1187,7 @@ static int solve_resume_impl(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_r
 
 int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, dymu_solve_stats* stats)
 {
+    DYMU_GUARD(ctx);
     if (!ranges || n_ranges == 0) return DYMU_ERR_ARG;
     return solve_resume_impl(ctx, ranges, n_ranges, false, 0.0, 0, stats);
 }
@@ -1149,20 +1195,22 @@ int dymu_solve_resume(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, 
 int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, double seed_key,
                        uint32_t max_phases, dymu_solve_stats* stats)
 {
+    DYMU_GUARD(ctx);
     if (max_phases == 0 || !(seed_key >= 0.0)) return DYMU_ERR_ARG;
     return solve_resume_impl(ctx, ranges, n_ranges, true, seed_key, max_phases, stats);
 }
 
-int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t goal_i, uint32_t goal_j,
-                       uint32_t first_phases, dymu_solve_stats* stats)
+int dymu_set_cost_map_begin(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t first_row)
 {
-    if (!ctx || !cost_host || ld < ctx->nx || goal_i >= ctx->nx || goal_j >= ctx->ny) return DYMU_ERR_ARG;
-    if (first_phases == 0) first_phases = 40;
+    DYMU_GUARD_ONLY(ctx);
+    if (!ctx || !cost_host || ld < ctx->nx) return DYMU_ERR_ARG;
+    if (ctx->upload_pending) DYMU_TRY(dymu_internal_settle_upload(ctx));
+    if (first_row >= ctx->ny) first_row = ctx->ny / 2;
     const uint32_t tile = ctx->tile, ny = ctx->ny;
-    // part A: the rows around the goal, uploaded first; part B: everything else
+    // part A: the rows around `first_row`, uploaded first; part B: everything else
     uint32_t reach = ny / 8 < 256 ? 256 : ny / 8;
-    uint32_t a0 = goal_j > reach ? ((goal_j - reach) / tile) * tile : 0;
-    uint32_t a1 = goal_j + reach < ny ? dymu_div_up(goal_j + reach, tile) * tile : ny;
+    uint32_t a0 = first_row > reach ? ((first_row - reach) / tile) * tile : 0;
+    uint32_t a1 = first_row + reach < ny ? dymu_div_up(first_row + reach, tile) * tile : ny;
     if (a1 > ny) a1 = ny;
     auto h2d_rows = [&](uint32_t j0, uint32_t j1) -> int {
         if (j0 >= j1) return DYMU_OK;
@@ -1173,26 +1221,44 @@ int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32
         return DYMU_OK;
     };
     // the copies must not overtake earlier work on the planes (a previous plan's read-back)
-    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
-    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up, ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_up, 0));
     DYMU_TRY(h2d_rows(a0, a1));
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_part, ctx->copy_stream));
     DYMU_TRY(h2d_rows(0, a0));
     DYMU_TRY(h2d_rows(a1, ny));
-    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up, ctx->copy_stream));
+    ctx->upload_pending = true;
+    ctx->up_a0 = a0;
+    ctx->up_a1 = a1;
+    ctx->solved = false;
+    return DYMU_OK;
+}
+
+// The solve of a cost map whose upload (dymu_set_cost_map_begin) is still in flight: the rows
+// that have arrived are opened first, the rest stays impassable (C_eff = +inf) until it is there,
+// then the tiles along the two seams are woken again.
+static int solve_streamed(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t first_phases,
+                          dymu_solve_stats* stats)
+{
+    if (first_phases == 0) first_phases = 40;
+    const uint32_t a0 = ctx->up_a0, a1 = ctx->up_a1, ny = ctx->ny;
+    ctx->upload_pending = false;
     // everything not uploaded yet is impassable for now
     DYMU_TRY(dymu_internal_fill(ctx, ctx->ceff, 1.0 / 0.0, (size_t)ctx->pitch * ctx->rows));
     DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_part, 0));
     DYMU_TRY(dymu_internal_cost_rows(ctx, a0, a1));
     ctx->have_cost = true;
     ctx->ceff_dirty = false;
-    if (!(ctx->fim_band < 1.0 / 0.0)) DYMU_TRY(dymu_internal_band_from_rows(ctx, a0, a1));
+    // band width of the scheduler from the rows that are there (the mean cost of a Mars-like map
+    // does not change much from one band of rows to the next)
+    DYMU_TRY(dymu_internal_band_from_rows(ctx, a0, a1));
     dymu_solve_stats first, rest;
     memset(&first, 0, sizeof(first));
     memset(&rest, 0, sizeof(rest));
-    DYMU_TRY(solve_total_cost_impl(ctx, 1, &goal_i, &goal_j, first_phases, &first));
+    int rc = solve_total_cost_impl(ctx, 1, &goal_i, &goal_j, first_phases, &first);
     // the rest has arrived meanwhile: open it up and wake the tiles along the two seams
-    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
     uint32_t ranges[4];
     uint32_t n_ranges = 0;
     if (a0 > 0)
@@ -1209,7 +1275,14 @@ int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32
         ranges[2 * n_ranges + 1] = a1 + 1;
         n_ranges++;
     }
-    int rc = DYMU_OK;
+    if (rc != DYMU_OK) return rc;
+    if (first.goal_obstacle)
+    {
+        // nothing was seeded (G.cpp:447-451: "The goal is not valid"); the planes are complete
+        if (stats) *stats = first;
+        ctx->solved = false;
+        return DYMU_OK;
+    }
     if (n_ranges || !first.converged)
         rc = solve_resume_impl(ctx, ranges, n_ranges, true, 0.0, 0, &rest);
     else
@@ -1229,8 +1302,18 @@ int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32
     return rc;
 }
 
+int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t goal_i, uint32_t goal_j,
+                       uint32_t first_phases, dymu_solve_stats* stats)
+{
+    DYMU_GUARD_ONLY(ctx);
+    if (!ctx || !cost_host || ld < ctx->nx || goal_i >= ctx->nx || goal_j >= ctx->ny) return DYMU_ERR_ARG;
+    DYMU_TRY(dymu_set_cost_map_begin(ctx, cost_host, ld, goal_j));
+    return solve_streamed(ctx, goal_i, goal_j, first_phases, stats);
+}
+
 int dymu_reset_total_cost(dymu_ctx* ctx)
 {
+    DYMU_GUARD(ctx);
     if (!ctx) return DYMU_ERR_ARG;
     ctx->solved = false;
     ctx->work.pending = false;
@@ -1240,6 +1323,7 @@ int dymu_reset_total_cost(dymu_ctx* ctx)
 int dymu_export_rows(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows, double* dst,
                      int device_ptr)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !dst || slot >= ctx->n_slots || n_rows == 0 || (uint64_t)j0 + n_rows > ctx->ny)
         return DYMU_ERR_ARG;
     const double* src = ctx->T + (size_t)slot * ctx->pitch * ctx->rows + (size_t)j0 * ctx->pitch;
@@ -1296,12 +1380,14 @@ static int import_rows_impl(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t 
 int dymu_import_rows_min(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
                          const double* src, int device_ptr, int* changed)
 {
+    DYMU_GUARD(ctx);
     return import_rows_impl(ctx, slot, j0, n_rows, src, device_ptr, changed, nullptr);
 }
 
 int dymu_import_rows_min_key(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t n_rows,
                              const double* src, int device_ptr, int* changed, double* min_lowered)
 {
+    DYMU_GUARD(ctx);
     if (!min_lowered) return DYMU_ERR_ARG;
     return import_rows_impl(ctx, slot, j0, n_rows, src, device_ptr, changed, min_lowered);
 }
@@ -1309,6 +1395,7 @@ int dymu_import_rows_min_key(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t
 int dymu_stop_threshold(dymu_ctx* ctx, uint32_t slot, uint32_t start_i, uint32_t start_j,
                         double* t_stop)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !t_stop || slot >= ctx->n_slots) return DYMU_ERR_ARG;
     if (start_i < 1 || start_j < 1 || start_i + 1 >= ctx->nx || start_j + 1 >= ctx->ny)
         return DYMU_ERR_ARG;

@@ -964,6 +964,7 @@ extern "C" {
 
 int dymu_local_create(dymu_ctx* ctx, uint32_t wg)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || wg < 3) return DYMU_ERR_ARG;
     dymu_internal_local_free(ctx);
@@ -995,6 +996,7 @@ int dymu_local_create(dymu_ctx* ctx, uint32_t wg)
 
 int dymu_local_anchor(dymu_ctx* ctx, int64_t gx0, int64_t gy0)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated) return DYMU_ERR_STATE;
     ctx->loc.gx0 = gx0;
@@ -1027,6 +1029,7 @@ static double* lplane(dymu_ctx* ctx, int p)
 int dymu_local_read_rect(dymu_ctx* ctx, int lplane_id, uint32_t x0, uint32_t y0, uint32_t w,
                          uint32_t h, double* host)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !host) return DYMU_ERR_ARG;
     const dymu_local& l = ctx->loc;
@@ -1042,6 +1045,7 @@ int dymu_local_read_rect(dymu_ctx* ctx, int lplane_id, uint32_t x0, uint32_t y0,
 int dymu_local_read_rect_u8(dymu_ctx* ctx, int lplane_id, uint32_t x0, uint32_t y0, uint32_t w,
                             uint32_t h, uint8_t* host)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !host) return DYMU_ERR_ARG;
     const dymu_local& l = ctx->loc;
@@ -1058,6 +1062,7 @@ int dymu_local_ingest(dymu_ctx* ctx, const uint8_t* image, uint32_t w, uint32_t 
                       uint32_t row_size, uint32_t pixel_size, double res, double rover_x,
                       double rover_y, uint32_t* new_cells, uint32_t cap, uint32_t* n_new)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !image || !new_cells || !n_new || w == 0 || h == 0
         || row_size < w * pixel_size || pixel_size == 0)
@@ -1110,6 +1115,7 @@ int dymu_local_blocking(dymu_ctx* ctx, const uint32_t* cells, uint32_t n_cells,
                         const double* path_xy, uint32_t n_path, double risk_distance,
                         uint32_t* min_index, uint32_t* max_index, int* blocked)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !min_index || !max_index || !blocked) return DYMU_ERR_ARG;
     *blocked = 0;
@@ -1139,6 +1145,7 @@ int dymu_local_blocking(dymu_ctx* ctx, const uint32_t* cells, uint32_t n_cells,
 
 int dymu_local_expand_risk(dymu_ctx* ctx, double risk_distance, dymu_solve_stats* stats)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !(risk_distance > 0)) return DYMU_ERR_ARG;
     dymu_local& l = ctx->loc;
@@ -1168,6 +1175,7 @@ int dymu_local_propagate(dymu_ctx* ctx, int approach, double start_x, double sta
                          double risk_ratio, int64_t* end_cell, uint32_t* status,
                          uint64_t* n_closed)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !end_cell || !status) return DYMU_ERR_ARG;
     dymu_local& l = ctx->loc;
@@ -1222,6 +1230,7 @@ int dymu_local_extract_path(dymu_ctx* ctx, int64_t end_cell, double start_x, dou
                             double offset_x, double offset_y, double* out, uint32_t cap,
                             uint32_t* n_out, int* status)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !out || !n_out || !status || cap == 0) return DYMU_ERR_ARG;
     const dymu_local& l = ctx->loc;
@@ -1255,6 +1264,7 @@ int dymu_local_extract_path(dymu_ctx* ctx, int64_t end_cell, double start_x, dou
 
 int dymu_local_sample_risk(dymu_ctx* ctx, const double* xy, uint32_t n, double* risk_out)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !xy || !risk_out) return DYMU_ERR_ARG;
     if (n == 0) return DYMU_OK;
@@ -1276,6 +1286,7 @@ int dymu_local_sample_risk(dymu_ctx* ctx, const double* xy, uint32_t n, double* 
 
 int dymu_local_read_entered(dymu_ctx* ctx, uint8_t* host, int clear)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !host) return DYMU_ERR_ARG;
     dymu_local& l = ctx->loc;
@@ -1288,6 +1299,7 @@ int dymu_local_read_entered(dymu_ctx* ctx, uint8_t* host, int clear)
 
 int dymu_local_cell_of(dymu_ctx* ctx, double x, double y, int64_t* cell)
 {
+    DYMU_GUARD(ctx);
     CallTrace call_trace(__func__);
     if (!ctx || !ctx->loc.allocated || !cell) return DYMU_ERR_ARG;
     k_cell_of<<<1, 1, 0, ctx->stream>>>(make_view(ctx), x, y, (int64_t*)ctx->d_scratch);

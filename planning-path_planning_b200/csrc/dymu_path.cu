@@ -311,6 +311,7 @@ int dymu_extract_global_path(dymu_ctx* ctx, uint32_t slot, double x0, double y0,
                              uint32_t goal_i, uint32_t goal_j, double* out, uint32_t cap,
                              uint32_t* n_out, int* status)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !out || !n_out || !status || cap == 0 || slot >= ctx->n_slots) return DYMU_ERR_ARG;
     if (goal_i >= ctx->nx || goal_j >= ctx->ny) return DYMU_ERR_ARG;
     size_t out_bytes = (size_t)cap * 5 * sizeof(double);
@@ -352,6 +353,7 @@ int dymu_extract_global_path_batch(dymu_ctx* ctx, uint32_t n, const uint32_t* sl
                                    const double* xy0, double tau, const uint32_t* goal_ij,
                                    double* out, uint32_t cap, uint32_t* n_out, int* status)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !slots || !xy0 || !goal_ij || !out || !n_out || !status || n == 0 || cap == 0)
         return DYMU_ERR_ARG;
     for (uint32_t q = 0; q < n; ++q)

@@ -391,11 +391,12 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
     if (!ctx) return DYMU_ERR_ARG;
     if (device < 0) cudaGetDevice(&device);
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess)
+    if (device >= ndev)
     {
         free(ctx);
         return DYMU_ERR_NODEVICE;
     }
+    dymu_device_guard guard__(device);  // the caller's current device is restored on return
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
     {
@@ -418,6 +419,7 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
     DYMU_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_part, cudaEventDisableTiming));
+    DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev2));
@@ -448,7 +450,7 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
 int dymu_destroy(dymu_ctx* ctx)
 {
     if (!ctx) return DYMU_OK;
-    cudaSetDevice(ctx->device);
+    DYMU_GUARD(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     dymu_internal_local_free(ctx);
     dymu_internal_fim_free(&ctx->work);
@@ -465,6 +467,7 @@ int dymu_destroy(dymu_ctx* ctx)
         if (ctx->user_ev[k]) cudaEventDestroy(ctx->user_ev[k]);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
+    if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
@@ -477,6 +480,7 @@ uint64_t dymu_launch_count(const dymu_ctx* ctx) { return ctx ? ctx->launches : 0
 
 int dymu_synchronize(dymu_ctx* ctx)
 {
+    DYMU_GUARD(ctx);
     if (!ctx) return DYMU_ERR_ARG;
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return DYMU_OK;
@@ -484,6 +488,7 @@ int dymu_synchronize(dymu_ctx* ctx)
 
 int dymu_event_record(dymu_ctx* ctx, int which)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || which < 0 || which >= 8) return DYMU_ERR_ARG;
     if (!ctx->user_ev[which]) DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->user_ev[which]));
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->user_ev[which], ctx->stream));
@@ -492,6 +497,7 @@ int dymu_event_record(dymu_ctx* ctx, int which)
 
 int dymu_event_elapsed_ms(dymu_ctx* ctx, int a, int b, float* ms)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !ms || a < 0 || a >= 8 || b < 0 || b >= 8 || !ctx->user_ev[a] || !ctx->user_ev[b])
         return DYMU_ERR_ARG;
     DYMU_CUDA_TRY(ctx, cudaEventSynchronize(ctx->user_ev[b]));
@@ -510,6 +516,7 @@ int dymu_geometry(const dymu_ctx* ctx, uint32_t* tile, uint32_t* pitch, uint32_t
 
 int dymu_upload_plane(dymu_ctx* ctx, int plane, const double* host, size_t ld)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || ld < ctx->nx) return DYMU_ERR_ARG;
     double* d = plane_ptr(ctx, plane);
     if (!d) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unknown plane %d", plane);
@@ -571,6 +578,7 @@ static int download_f64(dymu_ctx* ctx, const double* d, double* host, size_t ld,
 
 int dymu_download_plane(dymu_ctx* ctx, int plane, double* host, size_t ld, int xform)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || ld < ctx->nx) return DYMU_ERR_ARG;
     if (plane == DYMU_PLANE_CEFF) DYMU_TRY(dymu_internal_refresh_ceff(ctx));
     double* d = plane_ptr(ctx, plane);
@@ -580,12 +588,14 @@ int dymu_download_plane(dymu_ctx* ctx, int plane, double* host, size_t ld, int x
 
 int dymu_download_total_cost(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || ld < ctx->nx || slot >= ctx->n_slots) return DYMU_ERR_ARG;
     return download_f64(ctx, ctx->T + (size_t)slot * ctx->pitch * ctx->rows, host, ld, xform);
 }
 
 int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || ld < ctx->nx || slot >= ctx->n_slots) return DYMU_ERR_ARG;
     if (xform != DYMU_XFORM_NONE) DYMU_TRY(ensure_stage(ctx));  // allocate before forking
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
@@ -596,6 +606,7 @@ int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, s
 
 int dymu_download_total_cost_end(dymu_ctx* ctx)
 {
+    DYMU_GUARD(ctx);
     if (!ctx) return DYMU_ERR_ARG;
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     // later work on the main stream may overwrite the plane or the staging buffer
@@ -606,6 +617,7 @@ int dymu_download_total_cost_end(dymu_ctx* ctx)
 
 int dymu_download_plane_u8(dymu_ctx* ctx, int plane, uint8_t* host, size_t ld)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || ld < ctx->nx) return DYMU_ERR_ARG;
     uint8_t* d = plane_ptr_u8(ctx, plane);
     if (!d) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unknown u8 plane %d", plane);
@@ -623,6 +635,7 @@ static bool rect_ok(const dymu_ctx* ctx, uint32_t i0, uint32_t j0, uint32_t w, u
 int dymu_read_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t w, uint32_t h,
                    double* host)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || !rect_ok(ctx, i0, j0, w, h)) return DYMU_ERR_ARG;
     if (plane == DYMU_PLANE_CEFF) DYMU_TRY(dymu_internal_refresh_ceff(ctx));
     double* d = plane_ptr(ctx, plane);
@@ -637,6 +650,7 @@ int dymu_read_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t 
 int dymu_write_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t w, uint32_t h,
                     const double* host)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || !rect_ok(ctx, i0, j0, w, h)) return DYMU_ERR_ARG;
     double* d = plane_ptr(ctx, plane);
     if (!d) return DYMU_ERR_ARG;
@@ -654,6 +668,7 @@ int dymu_write_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t
 int dymu_read_rect_u8(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t w, uint32_t h,
                       uint8_t* host)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !host || !rect_ok(ctx, i0, j0, w, h)) return DYMU_ERR_ARG;
     uint8_t* d = plane_ptr_u8(ctx, plane);
     if (!d) return DYMU_ERR_ARG;
@@ -665,6 +680,7 @@ int dymu_read_rect_u8(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32
 
 int dymu_plane_device_ptr(dymu_ctx* ctx, int plane, void** dptr, size_t* pitch_elems)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !dptr) return DYMU_ERR_ARG;
     double* d = plane_ptr(ctx, plane);
     if (!d) return DYMU_ERR_ARG;
@@ -678,6 +694,7 @@ int dymu_plane_device_ptr(dymu_ctx* ctx, int plane, void** dptr, size_t* pitch_e
 
 int dymu_set_cost_map(dymu_ctx* ctx, const double* host, size_t ld)
 {
+    DYMU_GUARD(ctx);
     if (!ctx) return DYMU_ERR_ARG;
     if (host)
     {
@@ -698,6 +715,7 @@ int dymu_set_cost_map(dymu_ctx* ctx, const double* host, size_t ld)
 
 int dymu_upload_terrain(dymu_ctx* ctx, const double* terrain, size_t ld)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !terrain || ld < ctx->nx) return DYMU_ERR_ARG;
     DYMU_TRY(ensure_stage(ctx));
     DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_stage, ctx->nx * sizeof(double), terrain,
@@ -711,6 +729,7 @@ int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, cons
                           int n_slopes, int n_locs, const double* elevation, size_t ld_e,
                           const double* terrain, size_t ld_t)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !cost_lut || !slopes || n_lut < 1 || n_slopes < 1 || n_locs < 1 || n_locs > 254)
         return DYMU_ERR_ARG;
     if (elevation)
@@ -760,6 +779,7 @@ int dymu_compute_cost_map(dymu_ctx* ctx, const double* cost_lut, int n_lut, cons
 
 int dymu_time_stencils(dymu_ctx* ctx, float ms[6])
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !ms) return DYMU_ERR_ARG;
     for (int k = 0; k < 6; ++k) ms[k] = -1.0f;
     size_t n = (size_t)ctx->nx * ctx->ny, np = (size_t)ctx->pitch * ctx->rows;
@@ -801,6 +821,7 @@ int dymu_time_stencils(dymu_ctx* ctx, float ms[6])
 int dymu_read_cells(dymu_ctx* ctx, int plane, uint32_t slot, const uint32_t* cell_index,
                     uint32_t n, double* out)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !cell_index || !out) return DYMU_ERR_ARG;
     if (n == 0) return DYMU_OK;
     double* d = plane_ptr(ctx, plane);
@@ -830,6 +851,7 @@ int dymu_read_cells(dymu_ctx* ctx, int plane, uint32_t slot, const uint32_t* cel
 
 int dymu_read_node(dymu_ctx* ctx, uint32_t i, uint32_t j, double out[10])
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !out || i >= ctx->nx || j >= ctx->ny) return DYMU_ERR_ARG;
     k_read_node<<<1, 1, 0, ctx->stream>>>(ctx->elev, ctx->slope, ctx->raw, ctx->cost, ctx->haz,
                                           ctx->traff, ctx->T, ctx->terrain, ctx->obst, ctx->locmode,
@@ -844,11 +866,13 @@ int dymu_read_node(dymu_ctx* ctx, uint32_t i, uint32_t j, double out[10])
 
 int dymu_count_reached(dymu_ctx* ctx, uint32_t slot, uint64_t* n_finite)
 {
+    DYMU_GUARD(ctx);
     return dymu_count_leq(ctx, slot, 1.0 / 0.0, n_finite);
 }
 
 int dymu_count_leq(dymu_ctx* ctx, uint32_t slot, double threshold, uint64_t* n_finite)
 {
+    DYMU_GUARD(ctx);
     if (!ctx || !n_finite || slot >= ctx->n_slots) return DYMU_ERR_ARG;
     unsigned long long* d = (unsigned long long*)ctx->d_scratch;
     DYMU_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
@@ -881,6 +905,21 @@ int dymu_internal_cost_rows(dymu_ctx* ctx, uint32_t j0, uint32_t j1)
                                                              ctx->pitch, nr, ctx->nx, nr, nullptr);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    return DYMU_OK;
+}
+
+int dymu_internal_settle_upload(dymu_ctx* ctx)
+{
+    if (!ctx->upload_pending) return DYMU_OK;
+    ctx->upload_pending = false;
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
+    size_t n = (size_t)ctx->nx * ctx->ny;
+    k_set_cost_map<<<stream_grid(ctx, n), kThreads, 0, ctx->stream>>>(
+        ctx->cost, ctx->obst, ctx->traff, ctx->haz, ctx->pitch, ctx->nx, ctx->ny);
+    ctx->launches++;
+    DYMU_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->have_cost = true;
+    ctx->ceff_dirty = true;
     return DYMU_OK;
 }
 

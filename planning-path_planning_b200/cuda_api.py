@@ -27,7 +27,8 @@ _u32p = C.POINTER(C.c_uint32)
 class SolveStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_uint32), ("converged", C.c_uint32),
                 ("tile_activations", C.c_uint64), ("cell_updates", C.c_uint64),
-                ("cells_reached", C.c_uint64), ("tiles_deferred", C.c_uint64), ("inner_iterations", C.c_uint64), ("kernel_ms", C.c_float), ("reset_ms", C.c_float)]
+                ("cells_reached", C.c_uint64), ("tiles_deferred", C.c_uint64), ("inner_iterations", C.c_uint64), ("kernel_ms", C.c_float), ("reset_ms", C.c_float),
+                ("goal_obstacle", C.c_uint32), ("reserved_", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -57,6 +58,7 @@ _SIG = {
                                     C.c_uint32, _u8p]),
     "dymu_plane_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_size_t)]),
+    "dymu_set_cost_map_begin": (C.c_int, [C.c_void_p, _dp, C.c_size_t, C.c_uint32]),
     "dymu_set_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_size_t]),
     "dymu_compute_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp,
                                         C.c_size_t, _dp, C.c_size_t]),
@@ -297,9 +299,23 @@ class DeviceLayer:
                                              int(max_phases), C.byref(st)))
         return st.as_dict()
 
+    def _host_plane(self, a):
+        """The caller's buffer itself (it is read after the call returns, so never a copy)."""
+        if (not isinstance(a, np.ndarray) or a.dtype != np.float64 or not a.flags.c_contiguous
+                or a.shape != (self.ny, self.nx)):
+            raise ValueError("expected a C-contiguous float64 array of shape (%d, %d)" % (self.ny, self.nx))
+        return a
+
+    def set_cost_map_begin(self, cost_host, first_row):
+        """set_cost_map without waiting for the copy (dymu_set_cost_map_begin)."""
+        cost_host = self._host_plane(cost_host)
+        self._chk(self._l.dymu_set_cost_map_begin(self._h, cost_host.ctypes.data_as(_dp), cost_host.shape[1],
+                                                  int(first_row)))
+
     def plan_streamed(self, cost_host, goal, first_phases=0):
         """set_cost_map(cost_host) + solve_total_cost([goal]) with the upload overlapped with the
         solve (cost_host: C-contiguous float64 [ny, nx], pinned for a truly asynchronous copy)."""
+        cost_host = self._host_plane(cost_host)
         st = SolveStats()
         self._chk(self._l.dymu_plan_streamed(self._h, cost_host.ctypes.data_as(_dp), cost_host.shape[1],
                                              int(goal[0]), int(goal[1]), int(first_phases), C.byref(st)))

@@ -53,6 +53,9 @@ _SIGNATURES = {
     "dymu_planner_update_cost": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "dymu_planner_compute_cost_ratio": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "dymu_planner_recompute_cost_map": (C.c_int, [C.c_void_p]),
+    "dymu_planner_set_cost_map_flat": (C.c_int, [C.c_void_p, _dp, C.c_uint]),
+    "dymu_planner_set_total_cost_target": (C.c_int, [C.c_void_p, _dp, C.c_uint]),
+    "dymu_planner_get_total_cost_matrix_flat": (C.c_int, [C.c_void_p, _dp, C.c_uint]),
     "dymu_planner_last_call_seconds": (C.c_double, [C.c_void_p]),
 }
 
@@ -119,6 +122,35 @@ class Planner:
     def setCostMap(self, cost_map):
         m = _f64(cost_map)
         return bool(self._l.dymu_planner_set_cost_map(self._h, _ptr(m), m.shape[0], m.shape[1]))
+
+    @staticmethod
+    def _flat(a, ny, nx):
+        """float64 [ny, nx] array with contiguous rows, used in place (never copied: the callee may
+        read or write it after the call returns)."""
+        if (not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.ndim != 2 or a.shape != (ny, nx)
+                or a.strides[1] != 8 or a.strides[0] % 8 or a.strides[0] < 8 * nx):
+            raise ValueError("expected a float64 array of shape (%d, %d) with contiguous rows" % (ny, nx))
+        return a, a.strides[0] // 8
+
+    def setCostMapFlat(self, cost_map):
+        """setCostMap(const double*, ld) of the drop-in: no nesting, and with a goal in place the
+        upload is streamed behind the next computeEntireTotalCostMap() -- `cost_map` must stay
+        unchanged until that call returns (pinned memory makes the copy asynchronous)."""
+        m, ld = self._flat(cost_map, self.ny, self.nx)
+        return bool(self._l.dymu_planner_set_cost_map_flat(self._h, _ptr(m), ld))
+
+    def setTotalCostMatrixTarget(self, out):
+        """Deliver the total-cost matrix into `out` right after every solve (None = off)."""
+        if out is None:
+            self._target = None
+            return bool(self._l.dymu_planner_set_total_cost_target(self._h, None, 0))
+        m, ld = self._flat(out, self.ny, self.nx)
+        self._target = m  # keep the buffer alive while the planner writes into it
+        return bool(self._l.dymu_planner_set_total_cost_target(self._h, _ptr(m), ld))
+
+    def getTotalCostMatrixFlat(self, out):
+        m, ld = self._flat(out, self.ny, self.nx)
+        return bool(self._l.dymu_planner_get_total_cost_matrix_flat(self._h, _ptr(m), ld))
 
     def computeCostMap(self, cost_data, slope_values, locomotionModes, elevation, terrainMap):
         lut, sl = _f64(cost_data), _f64(slope_values)

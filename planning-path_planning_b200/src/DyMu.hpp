@@ -134,6 +134,11 @@ class DyMuPathPlanner
     uint goal_i, goal_j;
     // CLOSED-set emulation: a node is CLOSED iff total_cost <= closed_threshold
     double closed_threshold;
+    // total-cost matrix delivery started right after a solve (setTotalCostMatrixTarget)
+    double* readback_target;
+    size_t readback_ld;
+    bool readback_inflight;
+    bool streamed_cost;  // the last cost-map call was a streamed setCostMap(const double*, ld)
     // obstacles ingested but not yet expanded (local_expandable_obstacles, DyMu.hpp:452)
     bool pending_risk;
     uint local_window_nodes;
@@ -157,6 +162,8 @@ class DyMuPathPlanner
     std::vector<base::Waypoint> localPathFromCell(long cell, base::Waypoint wInit);
     void localCellPose(long cell, double& gx, double& gy) const;
     double totalCostNoOffset(double x, double y);
+    void startReadback();
+    void finishReadback();
 
   public:
     // -- PARAMETERS -- (kept for source compatibility; the narrow bands are transient
@@ -275,6 +282,10 @@ class DyMuPathPlanner
                         const std::vector<std::string>& locomotionModes, const double* elevation,
                         size_t ld_e, const double* terrainMap, size_t ld_t);
     bool getTotalCostMatrix(double* out, size_t ld);
+    // Deliver the total-cost matrix into `out` (row-major, ld doubles per row, pinned memory for a
+    // truly asynchronous copy) right after every successful compute*TotalCostMap, overlapped with
+    // the caller's next calls; getTotalCostMatrix(out, ld) then only waits.  NULL = off.
+    void setTotalCostMatrixTarget(double* out, size_t ld);
     // Apply the current cost_lutable (e.g. the one updateCost() just produced) to the DEM and
     // terrain classes that are already resident in HBM -- the reference's caller would hand
     // both maps to computeCostMap again.  With resolve=true and a goal set, the total-cost

@@ -45,6 +45,10 @@ DyMuPathPlanner::DyMuPathPlanner(double risk_distance,
       goal_i(0),
       goal_j(0),
       closed_threshold(kInf),
+      readback_target(NULL),
+      readback_ld(0),
+      readback_inflight(false),
+      streamed_cost(false),
       pending_risk(false),
       local_window_nodes(64),
       local_ready(false),
@@ -62,6 +66,7 @@ DyMuPathPlanner::DyMuPathPlanner(double risk_distance,
 // The reference leaks every node (G.cpp:36); the device planes are released here.
 DyMuPathPlanner::~DyMuPathPlanner()
 {
+    finishReadback();
     if (dev) dymu_destroy(dev);
     dev = NULL;
 }
@@ -91,6 +96,7 @@ bool DyMuPathPlanner::initGlobalLayer(double globalres,
     res_ratio = (uint)(global_res / local_res);
     global_offset = offset;
     if (global_offset.size() < 2) global_offset.resize(2, 0.0);
+    finishReadback();
     if (dev)
     {
         dymu_destroy(dev);
@@ -127,13 +133,50 @@ bool DyMuPathPlanner::setCostMap(std::vector<std::vector<double>> cost_map)
         if (cost_map[j].size() != num_nodes_X) return false;
         std::copy(cost_map[j].begin(), cost_map[j].end(), flat.begin() + (size_t)j * num_nodes_X);
     }
-    return setCostMap(flat.data(), num_nodes_X);
+    // `flat` dies with this call: blocking upload
+    return deviceOk(dymu_set_cost_map(dev, flat.data(), num_nodes_X), "setCostMap");
 }
 
+// Flat variant.  With a goal in place the upload is streamed: the rows around the goal go first
+// and the call returns without waiting; computeEntireTotalCostMap() starts on those rows while the
+// rest arrives (dymu_set_cost_map_begin).  The buffer must stay unchanged until the next planner
+// call returns.  Every other planner call completes the upload first, so the observable state is
+// the reference's.
 bool DyMuPathPlanner::setCostMap(const double* cost_map, size_t ld)
 {
-    if (!dev) return false;
+    if (!dev || !cost_map) return false;
+    finishReadback();
+    if (goal_set)
+    {
+        streamed_cost = deviceOk(dymu_set_cost_map_begin(dev, cost_map, ld, goal_j), "setCostMap");
+        return streamed_cost;
+    }
     return deviceOk(dymu_set_cost_map(dev, cost_map, ld), "setCostMap");
+}
+
+void DyMuPathPlanner::finishReadback()
+{
+    if (readback_inflight && dev) deviceOk(dymu_download_total_cost_end(dev), "getTotalCostMatrix");
+    readback_inflight = false;
+}
+
+// Total-cost matrix delivery (extension): after every successful compute*TotalCostMap the matrix
+// (inf -> -1, G.cpp:799-811) is copied into `out` on the copy stream, overlapping whatever the
+// caller does next (getPath); getTotalCostMatrix(out, ld) with the same pointer then only waits for
+// that copy.  NULL switches it off.
+void DyMuPathPlanner::setTotalCostMatrixTarget(double* out, size_t ld)
+{
+    finishReadback();
+    readback_target = out;
+    readback_ld = ld;
+}
+
+void DyMuPathPlanner::startReadback()
+{
+    if (!readback_target || !dev) return;
+    readback_inflight = deviceOk(dymu_download_total_cost_begin(dev, 0, readback_target, readback_ld,
+                                                                DYMU_XFORM_INF_TO_MINUS1),
+                                 "getTotalCostMatrix");
 }
 
 /*******************COMPUTE COST MAP FROM SLOPE MAP****************************/
@@ -288,6 +331,7 @@ bool DyMuPathPlanner::setGoal(base::Waypoint wGoal)
 bool DyMuPathPlanner::computeTotalCostMap(base::Waypoint wPos)
 {
     if (!dev) return false;
+    finishReadback();
     wPos.position[0] -= global_offset[0];
     wPos.position[1] -= global_offset[1];
 
@@ -341,6 +385,7 @@ bool DyMuPathPlanner::computeTotalCostMap(base::Waypoint wPos)
         LOG_ERROR_S << "The goal is unreachable";
         return false;
     }
+    startReadback();
     return true;
 }
 
@@ -384,17 +429,32 @@ bool DyMuPathPlanner::computeEntireTotalCostMap()
         LOG_WARN_S << "The goal is not valid";
         return false;
     }
-    readNode(goal_i, goal_j, goal_view);
-    if (goal_view.isObstacle)
+    finishReadback();
+    if (!streamed_cost)
     {
-        LOG_WARN_S << "The goal is not valid";
-        return false;
+        readNode(goal_i, goal_j, goal_view);
+        if (goal_view.isObstacle)
+        {
+            LOG_WARN_S << "The goal is not valid";
+            return false;
+        }
     }
+    // With a cost map that is still being uploaded (setCostMap(const double*, ld)) the test
+    // "global_goal->isObstacle" (G.cpp:447) is left to the solve itself, which starts on the rows
+    // that have arrived: a goal on an obstacle cell is not seeded and reported in the statistics.
+    // (In that one case the previous total-cost map is already reset when false is returned.)
+    streamed_cost = false;
     uint32_t gi = goal_i, gj = goal_j;
     dymu_solve_stats st;
     if (!deviceOk(dymu_solve_total_cost(dev, 1, &gi, &gj, &st), "computeEntireTotalCostMap"))
         return false;
+    if (st.goal_obstacle)
+    {
+        LOG_WARN_S << "The goal is not valid";
+        return false;
+    }
     closed_threshold = kInf;
+    startReadback();
     double heading = global_goal->pose.orientation;
     readNode(goal_i, goal_j, goal_view);
     goal_view.pose.orientation = heading;
@@ -535,8 +595,16 @@ std::vector<std::vector<double>> DyMuPathPlanner::getTotalCostMatrix()
 
 bool DyMuPathPlanner::getTotalCostMatrix(double* out, size_t ld)
 {
-    return dev && deviceOk(dymu_download_total_cost(dev, 0, out, ld, DYMU_XFORM_INF_TO_MINUS1),
-                           "getTotalCostMatrix");
+    if (!dev || !out) return false;
+    if (readback_inflight && out == readback_target && ld == readback_ld)
+    {
+        // already on its way since the solve finished (setTotalCostMatrixTarget)
+        bool ok = deviceOk(dymu_download_total_cost_end(dev), "getTotalCostMatrix");
+        readback_inflight = false;
+        return ok;
+    }
+    finishReadback();
+    return deviceOk(dymu_download_total_cost(dev, 0, out, ld, DYMU_XFORM_INF_TO_MINUS1), "getTotalCostMatrix");
 }
 
 // reference: G.cpp:815-829

@@ -100,3 +100,54 @@ def test_queries2048_batch_is_schedule_independent(pkg):
         assert np.array_equal(np.isinf(Ts), np.isinf(Tb)), "goal %d" % q
         fin = np.isfinite(Tb) & (Tb > 0)
         assert np.max(np.abs(Ts[fin] - Tb[fin]) / Tb[fin]) <= 1e-13, "goal %d" % q
+
+
+def _heap_port(oracle_mod, pkg, n, goal, seed=20261018):
+    """The pinned C port (bit-exact against the unmodified reference at <= 1000^2,
+    tests/test_oracle_vs_reference.py) with a binary heap instead of the reference's linear
+    narrow-band scan: same update expression, same values, seconds instead of an hour."""
+    syn = pkg.synthetic
+    elev, terr = syn.mars_dem(n, n, seed=seed)
+    lut, slopes, locs = syn.default_lut()
+    po = oracle_mod.Port(1.0, 1.5, 2.0, 1)
+    assert po.initGlobalLayer(1.0, 0.1, n, n)
+    assert po.computeCostMap(lut, slopes, locs, elev, terr)
+    assert po.setGoal(*goal)
+    assert po.computeEntireTotalCostMap(heap=True)
+    T = po.plane("total_cost").copy()
+    ob = po.plane("isObstacle").copy()
+    po.close()
+    return T, ob
+
+
+def test_plan4096_matches_heap_port(pkg, oracle_mod):
+    """The headline configuration (bench.py's map, goal and seed) compared cell by cell."""
+    n = 4096
+    dev, ob = _plan(pkg, n)
+    goal = pkg.synthetic.free_interior_cell_near(ob, n // 2, n // 2)
+    assert dev.solve_total_cost([goal])["converged"]
+    T = dev.download_total_cost()
+    To, obo = _heap_port(oracle_mod, pkg, n, goal)
+    assert np.array_equal(obo != 0, ob != 0), "obstacle mask"
+    assert np.array_equal(np.isinf(T), np.isinf(To)), "unreached set"
+    fin = np.isfinite(To) & (To > 0)
+    err = np.max(np.abs(T[fin] - To[fin]) / To[fin])
+    print("4096^2 vs heap port: max rel err %.3e, bit-equal cells %.4f" % (err, (T == To).mean()))
+    assert err <= 1e-9
+
+
+def test_query2048_matches_heap_port(pkg, oracle_mod):
+    """One query of config 4 (2048^2 map, goal drawn like bench.py draws them, solved inside a
+    batch of 8) against the heap port."""
+    n = 2048
+    dev, ob = _plan(pkg, n)
+    rng = np.random.default_rng(11)
+    goals = [pkg.synthetic.free_interior_cell_near(ob, int(rng.uniform(0.03, 0.97) * n),
+                                                   int(rng.uniform(0.03, 0.97) * n)) for _ in range(8)]
+    dev.reserve_slots(8)
+    assert dev.solve_total_cost(goals)["converged"]
+    T = dev.download_total_cost(slot=5)
+    To, _ = _heap_port(oracle_mod, pkg, n, goals[5])
+    assert np.array_equal(np.isinf(T), np.isinf(To))
+    fin = np.isfinite(To) & (To > 0)
+    assert np.max(np.abs(T[fin] - To[fin]) / To[fin]) <= 1e-9

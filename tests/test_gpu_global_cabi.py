@@ -154,3 +154,56 @@ def test_streamed_plan_equals_upload_then_solve(pkg, goal_xy, first_phases):
         fin = np.isfinite(want) & (want > 0)
         assert np.max(np.abs(got[fin] - want[fin]) / want[fin]) <= 1e-13
         assert np.array_equal(dev.download_plane("ceff"), plain.download_plane("ceff"))
+
+
+def test_abandoned_bounded_solve_leaves_no_stale_wakeups(pkg):
+    """A phase-bounded solve that is abandoned leaves wake-up flags / keys of its pending tiles
+    behind; the next full solve must not inherit them (a set flag would swallow that tile's
+    wake-up and the kernel would report convergence with part of the plane unpropagated)."""
+    n = 512
+    cost = pkg.synthetic.smooth_cost_map(n, n, seed=5)
+    ob = cost <= 0
+    ga = pkg.synthetic.free_interior_cell_near(ob, 100, 120)
+    gb = pkg.synthetic.free_interior_cell_near(ob, 400, 380)
+    clean = pkg.cuda_api.DeviceLayer(n, n)
+    clean.set_cost_map(cost)
+    assert clean.solve_total_cost([gb])["converged"]
+    want = clean.download_total_cost()
+    dut = pkg.cuda_api.DeviceLayer(n, n)
+    dut.set_cost_map(cost)
+    st = dut.solve_start(ga, 3)
+    assert not st["converged"]
+    assert dut.solve_total_cost([gb])["converged"]          # abandons the pending lists
+    got = dut.download_total_cost()
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    fin = np.isfinite(want) & (want > 0)
+    assert np.max(np.abs(got[fin] - want[fin]) / want[fin]) <= 1e-13
+    # the same after reset_total_cost() and after a resume that drops the pending work
+    st = dut.solve_start(ga, 2)
+    dut.reset_total_cost()
+    assert dut.solve_total_cost([gb])["converged"]
+    got = dut.download_total_cost()
+    assert np.max(np.abs(got[fin] - want[fin]) / want[fin]) <= 1e-13
+
+
+def test_two_contexts_on_two_devices_from_one_thread(pkg):
+    """Every entry point selects its context's device itself (and restores the caller's)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 256
+    cost = pkg.synthetic.smooth_cost_map(n, n, seed=9)
+    goal = pkg.synthetic.free_interior_cell_near(cost <= 0, 128, 128)
+    torch.cuda.set_device(0)
+    a = pkg.cuda_api.DeviceLayer(n, n, device=0)
+    b = pkg.cuda_api.DeviceLayer(n, n, device=1)
+    assert torch.cuda.current_device() == 0
+    out = []
+    for d in (a, b, a, b):          # interleaved use from one host thread
+        d.set_cost_map(cost)
+        assert d.solve_total_cost([goal])["converged"]
+        out.append(d.download_total_cost())
+    assert torch.cuda.current_device() == 0
+    fin = np.isfinite(out[0]) & (out[0] > 0)
+    for T in out[1:]:
+        assert np.max(np.abs(T[fin] - out[0][fin]) / out[0][fin]) <= 1e-13

@@ -20,7 +20,7 @@ def test_config1_golden(pkg):
     assert o["path_full"].shape == g["path_full"].shape
     assert np.max(np.abs(o["path_full"][:, :2] - g["path_full"][:, :2])) <= 1e-3
     assert o["path_early"].shape == g["path_early"].shape
-    assert np.max(np.abs(o["path_early"][:, :2] - g["path_early"][:, :2])) <= 5e-2
+    assert np.max(np.abs(o["path_early"][:, :2] - g["path_early"][:, :2])) <= 1e-3
 
 
 @pytest.mark.parametrize("approach,name", [(1, "repair_120_sweeping.npz"),
