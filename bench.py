@@ -12,9 +12,12 @@ reset + tile-FIM kernel) + gradient-descent path extraction from a fixed start.
   value  : plans/s with the cost planes already resident in HBM (device time, CUDA events
            on the library's stream, max over ranks).  ms_per_step is BASELINE's "ms per
            4096^2 total-cost-map solve" (+ path).
-  e2e    : the same through the C ABI with HOST buffers inside the timed region: H2D of the
-           cost plane (setCostMap), solve, path, D2H of the total-cost matrix
-           (getTotalCostMatrix) every step.
+  e2e    : the same through the drop-in class (DyMuPathPlanner in libdymu_b200.so) with HOST
+           buffers inside the timed region: H2D of the cost plane (setCostMap), solve, path,
+           D2H of the total-cost matrix (getTotalCostMatrix) every step.  e2e_cabi is the same
+           work issued directly against the C ABI of include/dymu_cuda.h.
+  sub-objects config2_repair / queries2048 / dd16384: the other BASELINE configs, measured in
+           the same run (see their docstrings).
   N > 1  : one process per GPU (torchrun); every rank plans on its own copy of the map
            with its own goal -- independent queries, no data-path collective ("weak").
 
@@ -48,10 +51,14 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="plan4096", choices=["plan4096", "queries2048"],
-                    help="plan4096 = BASELINE configs[2] (default, the headline); queries2048 = "
-                         "configs[3]: batches of independent goal queries on one shared 2048^2 map, "
-                         "sharded across the ranks")
+    ap.add_argument("--workload", default="all",
+                    help="comma list of plan4096 (BASELINE configs[2], the headline metric/value), config2 "
+                         "(configs[1]: 1000^2 + local repair, both approaches, reference beside it), "
+                         "queries2048 (configs[3]: 1024 goal queries on a 2048^2 map, sharded over the "
+                         "ranks), dd16384 (configs[4]: one 16384^2 grid, domain-decomposed for N >= 2); "
+                         "default all -- the sub-benchmarks are reported as sub-objects of the one line")
+    ap.add_argument("--dd-size", type=int, default=16384)
+    ap.add_argument("--dd-phases", type=int, default=32)
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--seed", type=int, default=20261018)
@@ -273,32 +280,83 @@ def cpu_baseline_leg(pkg, elev, terr, lut, slopes, locs, n):
 # ---------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------
-def _measured_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_fim launch on this workload, from the
-    committed `ncu --set full` capture (profiles/); None when the summary is not there."""
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_k_fim_traffic.json")
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_fim launch on this workload from the
+    committed `ncu --set full` capture of this round (profiles/), with its capture date -- kept
+    beside the figure derived live from the kernel's own counters."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
-                               "r1_k_fim_traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
+        with open(NCU_TRAFFIC_FILE) as f:
+            d = json.load(f)
+        return {"dram_bytes_per_launch": float(d["dram_bytes_per_launch"]), "captured": d.get("captured"),
+                "source": os.path.relpath(NCU_TRAFFIC_FILE, ROOT)}
     except (OSError, KeyError, ValueError):
         return None
 
 
-def run_b200(args):
-    import torch
-    import dymu_b200
-    rank, local_rank, world = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    pkg = dymu_b200.load()
+def pin_rank(local_rank, world):
+    """Give every rank its own slice of the host cores before it allocates pinned buffers, so that
+    first-touch places them next to the cores that drive this GPU's copies."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, world))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return [mine[0], mine[-1]]
+    except (AttributeError, OSError):
+        return None
+
+
+class Dist:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank, self.local_rank, self.world = dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.on = self.world > 1
+        if self.on:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.on:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, values):
+        if not self.on:
+            return [float(v) for v in values]
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def gather(self, values):
+        """per-rank lists of floats -> list (rank order) on every rank"""
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        if not self.on:
+            return [[float(v) for v in t]]
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [[float(v) for v in o] for o in out]
+
+    def close(self):
+        if self.on:
+            self.dist.destroy_process_group()
+
+
+def headline_plan4096(args, D, pkg, affinity):
+    """configs[2]: the line's metric/value/e2e/roofline."""
+    torch = D.torch
+    rank, world = D.rank, D.world
     n = args.size
     elev, terr, lut, slopes, locs = build_workload(pkg, n, args.seed)
-    dev = pkg.cuda_api.DeviceLayer(n, n, 1.0, 0.1, device=local_rank)
+    dev = pkg.cuda_api.DeviceLayer(n, n, 1.0, 0.1, device=D.local_rank)
     dev.compute_cost_map(lut, slopes, len(locs), elev, terr)
     ob = dev.download_plane_u8("obstacle")
     syn = pkg.synthetic
@@ -323,19 +381,12 @@ def run_b200(args):
     reached = dev.count_reached()
     assert reached >= 0.90 * n * n, "goal is walled in: only %.3f of the map reached" % (
         reached / float(n * n))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    barrier()
+    sampler = ClockSampler(D.local_rank)
+    D.barrier()
     if rank == 0:
         sampler.start()
     launches0 = dev.launches
-    kernel_ms, tiles, updates, outers = [], [], [], []
+    kernel_ms, tiles, updates, outers, written = [], [], [], [], []
     dev.event_record(0)
     for _ in range(args.steps):
         st, nwp, status = plan()
@@ -343,58 +394,105 @@ def run_b200(args):
         tiles.append(st["tile_activations"])
         updates.append(st["cell_updates"])
         outers.append(st["outer_iterations"])
+        written.append(st["cells_written"])
     dev.event_record(1)
     total_ms = dev.event_elapsed_ms(0, 1)
     launches = dev.launches - launches0
-    barrier()
+    D.barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end arm: host buffers in, host matrix out, every step --------------------
+    # ---- end-to-end, C ABI: host buffers in, host matrix out, every step ----------------
     cost_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
-    dev.download_plane("cost", out=cost_host.numpy())
+    # the host-side input of a plan is the cost map a caller would hand to setCostMap: obstacles
+    # carry cost <= 0 (getGlobalCostMatrix convention, G.cpp:815-829), so it is self-contained
+    dev.download_plane("cost", xform=pkg.cuda_api.XFORM_EFFECTIVE_COST, out=cost_host.numpy())
     t_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
 
-    def plan_e2e():
-        # setCostMap + computeEntireTotalCostMap from the pinned host buffer; the upload of the
-        # rows away from the goal runs on the copy stream behind the first solver phases
+    def plan_cabi():
         dev.plan_streamed(cost_host.numpy(), goal)
-        # getTotalCostMatrix read-back runs on the copy stream while the path is extracted
         dev.download_total_cost_begin(t_host.numpy(), xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
         dev.extract_global_path(float(start[0]), float(start[1]), 0.4, goal[0], goal[1])
         dev.download_total_cost_end()
 
     for _ in range(min(2, args.warmup)):
-        plan_e2e()
-    barrier()
+        plan_cabi()
+    D.barrier()
     dev.event_record(2)
     for _ in range(args.steps):
-        plan_e2e()
+        plan_cabi()
     dev.event_record(3)
-    e2e_ms = dev.event_elapsed_ms(2, 3)
-    barrier()
+    cabi_ms = dev.event_elapsed_ms(2, 3)
+    D.barrier()
+    t_check = t_host.numpy().copy() if rank == 0 else None
+    # copy rates of this rank's link, timed alone (what the e2e step has to hide)
+    dev.event_record(4)
+    dev.upload_plane("cost", cost_host.numpy())
+    dev.event_record(5)
+    dev.download_total_cost(out=t_host.numpy())
+    dev.event_record(6)
+    h2d_gbs = n * n * 8 / (dev.event_elapsed_ms(4, 5) * 1e-3) / 1e9
+    d2h_gbs = n * n * 8 / (dev.event_elapsed_ms(5, 6) * 1e-3) / 1e9
+    dev.close()
 
-    if distributed:
-        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
+    # ---- end-to-end, through the drop-in class (the call a user of the reference makes) ----
+    # DyMuPathPlanner::setCostMap(const double*, ld) -> computeEntireTotalCostMap() -> getPath()
+    # -> getTotalCostMatrix(double*, ld) via libdymu_b200.so
+    pl = pkg.DyMuPathPlanner(1.0, 1.5, 2.0, pkg.planner_api.SWEEPING)
+    assert pl.initGlobalLayer(1.0, 0.1, n, n), "initGlobalLayer failed"
+    assert pl.setCostMapFlat(cost_host.numpy())
+    assert pl.setGoal(float(goal[0]), float(goal[1]))
+    assert pl.setTotalCostMatrixTarget(t_host.numpy())
+
+    def plan_class():
+        ok = pl.setCostMapFlat(cost_host.numpy())
+        ok = ok and pl.computeEntireTotalCostMap()
+        path = pl.getPath(float(start[0]), float(start[1]))
+        ok = ok and pl.getTotalCostMatrixFlat(t_host.numpy())
+        assert ok
+        return len(path)
+
+    for _ in range(max(1, min(2, args.warmup))):
+        nwp_class = plan_class()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nwp_class = plan_class()
+    torch.cuda.synchronize()
+    class_ms = (time.perf_counter() - t0) * 1e3
+    D.barrier()
+    if rank == 0:
+        # the class delivered the same matrix as the C-ABI arm (inf -> -1 in both); getPath appends
+        # the goal waypoint (G.cpp:589-611), the raw C-ABI path does not
+        with np.errstate(invalid="ignore"):
+            same = np.array_equal(t_check < 0, t_host.numpy() < 0)
+        assert same and abs(nwp_class - nwp) <= 1, ("class e2e arm disagrees with the C-ABI arm: unreached mask equal "
+                                           "%s (%d vs %d cells), waypoints %d vs %d"
+                                           % (same, int((t_check < 0).sum()), int((t_host.numpy() < 0).sum()),
+                                              nwp_class, nwp))
+    pl.setTotalCostMatrixTarget(None)
+    pl.close()
+
+    total_ms, cabi_ms, class_ms = D.max([total_ms, cabi_ms, class_ms])
+    rates = D.gather([h2d_gbs, d2h_gbs])
     if rank != 0:
-        if distributed:
-            dist.destroy_process_group()
-        return 0
-
+        return None
     ms_per_step = total_ms / args.steps
     value = world * 1e3 / ms_per_step
-    e2e_value = world * 1e3 / (e2e_ms / args.steps)
     peak, peak_src = measured_peak()
     k_ms = statistics.mean(kernel_ms)
     # (i) 24 B per cell update (read C_eff, read T, write T) x the cell
     # updates one launch performs -- the figure `achieved` is built from; (ii) 16 B per reached
-    # cell per solve, the lower bound.  The tile-level figure counts only what an activation has
-    # to move between HBM/L2 and shared memory.
+    # cell per solve, the lower bound.
     algo_bytes = statistics.mean(updates) * CELL_SWEEP_BYTES
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    tile_bytes = statistics.mean(tiles) * tile * tile * CELL_SWEEP_BYTES
     solve_bytes = SOLVE_BYTES_PER_CELL * reached
+    # live DRAM-side figure from the kernel's own counters: every activation stages T, C_eff and
+    # the 4 x 32 halo cells of its tile, and stores back the cells that changed.  This is what
+    # crosses between L2 and the SMs -- an upper bound of the DRAM traffic (part of it hits in
+    # the 126 MB L2); the ncu capture of this round sits beside it.
+    staged = statistics.mean(tiles) * (2 * tile * tile + 4 * tile) * 8
+    stored = statistics.mean(written) * 8
+    ncu = _ncu_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -407,74 +505,155 @@ def run_b200(args):
             "reached_fraction": reached / float(n * n), "waypoints": nwp,
             "l2": "inputs larger than L2 (each fp64 plane %.0f MB > 126 MB L2)" % (n * n * 8 / 1e6),
             "parallelism": "1 independent plan per GPU, no collective",
+            "rank_core_affinity": affinity,
         },
+        "solve_ms_per_4096_map": k_ms,
         "solve_kernel_ms": k_ms,
         "gcell_updates_per_s": statistics.mean(updates) / (k_ms * 1e-3) / 1e9,
         "updates_per_cell": statistics.mean(updates) / float(n * n),
+        "activations_per_tile": statistics.mean(tiles) / float((pitch // tile) * (rows // tile)),
         "outer_iterations": statistics.mean(outers),
         "roofline": {
             "bound": "hbm", "kernel": "k_fim<%d,0> (tile FIM sweep)" % tile,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": _measured_traffic(), "peak_source": peak_src,
+            "traffic": (ncu or {}).get("dram_bytes_per_launch"),
+            "traffic_ncu": ncu,
+            "traffic_live": {"bytes": staged + stored, "staged_bytes": staged, "stored_bytes": stored,
+                             "gbs": (staged + stored) / (k_ms * 1e-3) / 1e9,
+                             "definition": "tile activations x (2 x %d^2 + 4 x %d) x 8 B staged + cells "
+                                           "written back x 8 B, both counted by the kernel in this run; "
+                                           "L2<->SM bytes, an upper bound of the DRAM bytes" % (tile, tile)},
+            "dram_frac": (((ncu or {}).get("dram_bytes_per_launch") or (staged + stored))
+                          / (k_ms * 1e-3) / 1e9 / peak),
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes,
             "definition": "SURVEY 8(d)(i): cell updates x 24 B (read C_eff, read T, write T) / kernel "
-                          "time.  The updates of an activated tile run in shared memory, so the DRAM "
-                          "bytes actually moved (`traffic`, ncu) are ~1 %% of this: the kernel is "
-                          "bounded by dependency latency and fp64 issue, not by HBM (DESIGN.md "
-                          "section 5)",
-            "tile_level": {"bytes": tile_bytes, "achieved": tile_bytes / (k_ms * 1e-3) / 1e9,
-                           "frac": tile_bytes / (k_ms * 1e-3) / 1e9 / peak,
-                           "definition": "tile activations x %d^2 cells x 24 B: what has to cross "
-                                         "between L2/HBM and shared memory" % tile},
+                          "time.  The updates of an activated tile run in shared memory, so `frac` "
+                          "measures on-chip stencil work, not HBM use: `dram_frac` (measured DRAM bytes "
+                          "/ time / peak) is the honest HBM figure and it is < 1 %% -- the solve is "
+                          "bounded by dependency latency (DESIGN.md section 5)",
             "solve_level": {"bytes": solve_bytes,
                             "achieved": solve_bytes / (k_ms * 1e-3) / 1e9,
                             "frac": solve_bytes / (k_ms * 1e-3) / 1e9 / peak,
                             "definition": "SURVEY 8(d)(ii): 16 B x reached cells / solve time "
                                           "(lower bound: 41 us at peak)"},
         },
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + nwp * 40},
+        "e2e": {"value": world * 1e3 / (class_ms / args.steps), "unit": UNIT,
+                "ms_per_step": class_ms / args.steps,
+                "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + nwp * 32,
+                "api": "DyMuPathPlanner::setCostMap(const double*, ld) -> computeEntireTotalCostMap() -> "
+                       "getPath() -> getTotalCostMatrix(double*, ld) through libdymu_b200.so, pinned "
+                       "host buffers, wall clock around the synchronous calls (max over ranks)"},
+        "e2e_cabi": {"value": world * 1e3 / (cabi_ms / args.steps), "unit": UNIT,
+                     "ms_per_step": cabi_ms / args.steps,
+                     "api": "dymu_plan_streamed + dymu_download_total_cost_begin/_end + "
+                            "dymu_extract_global_path (include/dymu_cuda.h), CUDA events"},
+        "link_gbs_per_rank": [{"h2d": r[0], "d2h": r[1]} for r in rates],
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    # the streaming (HBM-bound) stencil kernels of the same path, timed once each
+    return line, (elev, terr, lut, slopes, locs)
+
+
+def stencil_leg(args, D, pkg):
+    """the streaming (HBM-bound) stencil kernels of the same path, timed once each"""
+    n = args.size
+    peak, _ = measured_peak()
     try:
+        dev = pkg.cuda_api.DeviceLayer(n, n, 1.0, 0.1, device=D.local_rank)
+        dev.set_cost_map(np.ones((n, n)))
+        tile, pitch, rows = dev.geometry()
         sm = dev.time_stencils()
+        dev.close()
         cells, pcells = float(n * n), float(pitch * rows)
         spec = [("k_fill_f64 (total-cost reset)", sm[0], 8 * cells),
                 ("k_ceff (C_eff build)", sm[1], 33 * pcells),
                 ("k_readback (inf -> -1)", sm[2], 16 * cells),
                 ("k_set_cost_map (obstacle mask)", sm[3], 8 * cells)]
-        line["stencils"] = {nm: {"ms": ms_, "algorithmic_bytes": b, "gbs": b / (ms_ * 1e-3) / 1e9,
-                                 "frac_of_measured_peak": b / (ms_ * 1e-3) / 1e9 / peak}
-                            for nm, ms_, b in spec if ms_ > 0}
-    except Exception as e:  # timing helper is informational
-        line["stencils"] = {"error": str(e)}
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_leg(pkg, elev, terr, lut, slopes, locs, n)
-    print(json.dumps(line))
-    if distributed:
-        dist.destroy_process_group()
-    return 0
+        return {nm: {"ms": ms_, "algorithmic_bytes": b, "gbs": b / (ms_ * 1e-3) / 1e9,
+                     "frac_of_measured_peak": b / (ms_ * 1e-3) / 1e9 / peak}
+                for nm, ms_, b in spec if ms_ > 0}
+    except Exception as e:  # informational
+        return {"error": str(e)}
 
 
-def run_queries(args):
+def config2_repair(args, D, pkg):
+    """configs[1]: 1000x1000 global layer + local repair after injected obstacles, both repairing
+    approaches, through DyMuPathPlanner; the UNMODIFIED reference is timed beside it in the same
+    process on identical calls (rank 0 only: the local layer does not shard -- replicas only)."""
+    if D.rank != 0:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenarios as sc
+    syn = pkg.synthetic
+    n = 1000
+    out = {"workload": "configs[1]: 1000x1000 Mars-like map, goal (800,800), start (200,200), "
+                       "computeTotalCostMap + getPath, 120x120 px frame with an obstacle disc on path[10] "
+                       "+ 3 random discs (seed 7), computeLocalPlanning", "approaches": {}}
+    ref_lib = None
+    if not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle
+            ref_lib = oracle.reference() if oracle.have_reference() else None
+        except Exception:
+            ref_lib = None
+    for approach, name in ((pkg.planner_api.SWEEPING, "SWEEPING"), (pkg.planner_api.CONSERVATIVE, "CONSERVATIVE")):
+        rec = {}
+        reps = 5
+        t_rep, traj = [], None
+        for _ in range(reps):        # a repair changes the planner's state: fresh planner per run
+            p = sc.make_planner(pkg.DyMuPathPlanner, approach, n, n)
+            g = sc.global_scenario(p, syn, n, n, seed=args.seed)
+            c = g["path"][0, :2]
+            img = _config2_frame(syn, g["path"], 7)
+            t0 = time.perf_counter()
+            repaired, traj, _ = p.computeLocalPlanning(c[0], c[1], img, 0.1)
+            t_rep.append((time.perf_counter() - t0) * 1e3)
+            ridx = p.getReconnectingIndex()
+            p.close()
+        rec["b200"] = {"repair_ms": statistics.median(t_rep), "repair_ms_all": t_rep, "repaired": bool(repaired),
+                       "trajectory_waypoints": int(len(traj)), "reconnecting_index": int(ridx)}
+        if ref_lib is not None:
+            p = sc.make_planner(ref_lib.DyMuPathPlanner, approach, n, n)
+            t0 = time.perf_counter()
+            g = sc.global_scenario(p, syn, n, n, seed=args.seed)
+            t_global_ref = time.perf_counter() - t0
+            c = g["path"][0, :2]
+            img = _config2_frame(syn, g["path"], 7)
+            t0 = time.perf_counter()
+            repaired_r, traj_r, _ = p.computeLocalPlanning(c[0], c[1], img, 0.1)
+            t_ref = (time.perf_counter() - t0) * 1e3
+            rec["reference"] = {"repair_ms": t_ref, "repaired": bool(repaired_r),
+                                "trajectory_waypoints": int(len(traj_r)),
+                                "reconnecting_index": int(p.getReconnectingIndex()),
+                                "global_setup_s": t_global_ref, "cores": 1, "kind": "reference"}
+            rec["speedup_vs_reference"] = t_ref / rec["b200"]["repair_ms"]
+            same = (traj_r.shape == traj.shape and float(np.max(np.abs(traj_r[:, :2] - traj[:, :2]))) <= 1e-3
+                    and rec["reference"]["reconnecting_index"] == rec["b200"]["reconnecting_index"])
+            rec["same_trajectory_as_reference"] = bool(same)
+            p.close()
+        out["approaches"][name] = rec
+    return out
+
+
+def _config2_frame(syn, path, seed):
+    c = path[0, :2]
+    d = path[min(10, len(path) - 2), :2]
+    rng = np.random.default_rng(seed)
+    discs = [(d[0], d[1], 0.8)]
+    discs += [(c[0] + rng.uniform(-4, 4), c[1] + rng.uniform(-4, 4), rng.uniform(0.2, 0.5)) for _ in range(3)]
+    return syn.obstacle_frame(120, 120, 0.1, c, discs)
+
+
+def queries2048(args, D, pkg):
     """configs[3]: `--queries` independent goal queries (full solve + path each) on one shared
     2048x2048 map, block-sharded over the ranks (no data-path collective), `--batch` goals per
-    launch.  One JSON line; a step = this rank's whole share."""
-    import torch
-    import dymu_b200
-    rank, local_rank, world = dist_env()
-    torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    pkg = dymu_b200.load()
+    launch.  Strong scaling: the total work is fixed."""
     syn, sh = pkg.synthetic, pkg.sharding
     n = 2048
     elev, terr, lut, slopes, locs = build_workload(pkg, n, args.seed)
-    dev = pkg.cuda_api.DeviceLayer(n, n, 1.0, 0.1, device=local_rank)
+    dev = pkg.cuda_api.DeviceLayer(n, n, 1.0, 0.1, device=D.local_rank)
     dev.compute_cost_map(lut, slopes, len(locs), elev, terr)
     ob = dev.download_plane_u8("obstacle")
     rng_g, rng_s = np.random.default_rng(11), np.random.default_rng(13)
@@ -482,48 +661,131 @@ def run_queries(args):
                                          int(rng_g.uniform(0.03, 0.97) * n)) for _ in range(args.queries)]
     starts = [syn.free_interior_cell_near(ob, int(rng_s.uniform(0.03, 0.97) * n),
                                           int(rng_s.uniform(0.03, 0.97) * n)) for _ in range(args.queries)]
-    mine = list(sh.shard_queries(args.queries, world, rank))
+    mine = list(sh.shard_queries(args.queries, D.world, D.rank))
     B = max(1, min(args.batch, len(mine)))
     dev.reserve_slots(B)
 
-    def share():
-        nwp = 0
-        for lo in range(0, len(mine), B):
-            idx = mine[lo:lo + B]
-            dev.solve_total_cost([goals[q] for q in idx])
+    def run(idx_all):
+        nwp, kms = 0, 0.0
+        for lo in range(0, len(idx_all), B):
+            idx = idx_all[lo:lo + B]
+            st = dev.solve_total_cost([goals[q] for q in idx])
+            kms += st["kernel_ms"]
             paths, _ = dev.extract_global_path_batch(
                 list(range(len(idx))), [[float(starts[q][0]), float(starts[q][1])] for q in idx], 0.4,
                 [goals[q] for q in idx], cap=1 << 14)
             nwp += sum(len(w) for w in paths)
-        return nwp
+        return nwp, kms
 
-    for _ in range(max(1, min(args.warmup, 1))):
-        share()
-    torch.cuda.synchronize()
-    if distributed:
-        dist.barrier()
+    run(mine[:B])                      # warm-up: one batch
+    D.barrier()
     launches0 = dev.launches
     dev.event_record(0)
-    for _ in range(args.steps):
-        nwp = share()
+    nwp, kms = run(mine)
     dev.event_record(1)
     ms = dev.event_elapsed_ms(0, 1)
     launches = dev.launches - launches0
-    if distributed:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-        dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": args.queries * args.steps / (ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "configs[3]: %d independent goal queries (solve + path) on one shared "
-                                   "2048x2048 map, %d goals per launch, block-sharded over %d GPU(s)"
-                                   % (args.queries, B, world), "seed": args.seed},
-            "gpu_launches": int(launches), "waypoints_last_share": nwp}))
+    dev.close()
+    ms, kms = D.max([ms, kms])
+    if D.rank != 0:
+        return None
+    return {"workload": "configs[3]: %d independent goal queries (solve + path) on one shared 2048x2048 "
+                        "map, %d goals per launch, block-sharded over %d GPU(s)" % (args.queries, B, D.world),
+            "plans_per_s": args.queries / (ms * 1e-3), "ms_total": ms, "max_rank_solve_kernel_ms": kms,
+            "queries": args.queries, "n_gpus": D.world, "scaling": "strong", "gpu_launches_rank0": int(launches),
+            "waypoints_rank0": int(nwp)}
+
+
+def dd16384(args, D, pkg):
+    """configs[4]: one 16384x16384 grid (periodic 4096^2 fBm cost tile, goal near the centre).
+    1 GPU: the plain single-grid solve (scaling base).  N >= 2: row strips, one per rank, halo rows
+    exchanged between bounded bursts of solver phases (sharding.dd_solve_pipelined); every rank
+    then solves the whole grid alone and checks its strip against it (`verified`)."""
+    torch = D.torch
+    sh, api, syn = pkg.sharding, pkg.cuda_api, pkg.synthetic
+    n, base = args.dd_size, min(4096, args.dd_size)
+    tile = syn.smooth_cost_map(base, base, seed=args.seed, obstacle_fraction=0.03)   # periodic (FFT fBm)
+    reps = n // base
+    g0 = syn.free_interior_cell_near(tile <= 0, base // 2, base // 2)
+    goal = (g0[0] + (reps // 2) * base, g0[1] + (reps // 2) * base)
+    whole = api.DeviceLayer(n, n, device=D.local_rank)
+    whole.set_cost_map(np.tile(tile, (reps, reps)))
+    whole.solve_total_cost([goal])                                   # warm-up
+    st1 = whole.solve_total_cost([goal])
+    single_ms = st1["kernel_ms"]
+    rec = {"workload": "configs[4]: %dx%d single grid, goal near the centre" % (n, n), "n_gpus": D.world,
+           "single_gpu_solve_ms": None, "strips": None}
+    if D.world == 1:
+        whole.close()
+        rec["single_gpu_solve_ms"] = single_ms
+        rec["updates_per_cell"] = st1["cell_updates"] / float(n * n)
+        return rec
+    lay = sh.StripLayout(n, D.world, D.rank)
+    rows = np.arange(lay.r0, lay.r1) % base
+    strip = sh.CudaStrip(api, lay, n, np.tile(tile[rows], (1, reps)), D.local_rank, torch)
+    comm = sh.TorchComm(D.rank, D.world, torch.device("cuda", D.local_rank))
+    times, rounds, kms = [], 0, 0.0
+    for _ in range(2):
+        n0 = len(strip.stats)
+        D.barrier()
+        t0 = time.perf_counter()
+        rounds = sh.dd_solve_pipelined(strip, comm, goal, args.dd_phases)
+        torch.cuda.synchronize()
+        D.barrier()
+        times.append((time.perf_counter() - t0) * 1e3)
+        kms = sum(s["kernel_ms"] for s in strip.stats[n0:])
+    T1 = whole.download_total_cost()[lay.r0:lay.r1]
+    Tk = strip.own_rows()
+    fin = np.isfinite(T1) & (T1 > 0)
+    err = float(np.max(np.abs(Tk[fin] - T1[fin]) / T1[fin])) if fin.any() else 0.0
+    good = 1.0 if (np.array_equal(np.isinf(Tk), np.isinf(T1)) and err <= 1e-12) else 0.0
+    whole.close()
+    wall, kmax, single, neg_good, errmax = D.max([min(times), kms, single_ms, -good, err])
+    if D.rank != 0:
+        return None
+    rec["single_gpu_solve_ms"] = single
+    rec["strips"] = {"wall_ms": wall, "max_rank_kernel_ms": kmax, "exchange_rounds": rounds,
+                     "phases_per_round": args.dd_phases, "verified": bool(neg_good == -1.0),
+                     "max_rel_err_vs_single_grid": errmax,
+                     "driver": "sharding.dd_solve_pipelined (torch.distributed point-to-point rows)"}
+    return rec
+
+
+def run_b200(args):
+    import dymu_b200
+    D = Dist()
+    affinity = pin_rank(D.local_rank, D.world)
+    pkg = dymu_b200.load()
+    want = set(args.workload.split(",")) if args.workload != "all" else {"plan4096", "config2", "queries2048",
+                                                                        "dd16384"}
+    line, maps = None, None
+    if "plan4096" in want:
+        res = headline_plan4096(args, D, pkg, affinity)
+        if D.rank == 0:
+            line, maps = res
+            line["stencils"] = stencil_leg(args, D, pkg)
+            if not args.no_cpu_baseline and D.world == 1:
+                line["cpu_baseline"] = cpu_baseline_leg(pkg, *maps, args.size)
+    elif D.rank == 0:
+        line = {"metric": METRIC, "unit": UNIT, "n_gpus": D.world, "note": "sub-benchmarks only"}
+    extra = {}
+    for name, fn in (("config2_repair", config2_repair), ("queries2048", queries2048), ("dd16384", dd16384)):
+        key = {"config2_repair": "config2", "queries2048": "queries2048", "dd16384": "dd16384"}[name]
+        if key not in want:
+            continue
+        t0 = time.perf_counter()
+        try:
+            rec = fn(args, D, pkg)
+        except Exception as e:  # a sub-benchmark must not take the headline line down with it
+            rec = {"error": "%s: %s" % (type(e).__name__, e)}
+        D.barrier()
+        if D.rank == 0 and rec is not None:
+            rec["bench_seconds"] = time.perf_counter() - t0
+            extra[name] = rec
+    if D.rank == 0:
+        line.update(extra)
+        print(json.dumps(line))
+    D.close()
     return 0
 
 
@@ -531,4 +793,4 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         sys.exit(run_reference(a))
-    sys.exit(run_queries(a) if a.workload == "queries2048" else run_b200(a))
+    sys.exit(run_b200(a))

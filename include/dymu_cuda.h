@@ -73,6 +73,7 @@ typedef struct dymu_solve_stats
     uint32_t goal_obstacle;     /* goals that sit on an obstacle cell and were therefore not seeded
                                    ("The goal is not valid", G.cpp:370-374) */
     uint32_t reserved_;
+    uint64_t cells_written;     /* cells whose value was stored back to the plane (8 B each) */
 } dymu_solve_stats;
 
 /* ---- context ---------------------------------------------------------- */
@@ -250,7 +251,13 @@ int dymu_extract_global_path_batch(dymu_ctx* ctx, uint32_t n, const uint32_t* sl
 #define DYMU_LPLANE_U8_OBSTACLE 0
 #define DYMU_LPLANE_U8_STATE 1
 int dymu_local_create(dymu_ctx* ctx, uint32_t wg);
-int dymu_local_anchor(dymu_ctx* ctx, int64_t gx0, int64_t gy0); /* clears the window */
+int dymu_local_anchor(dymu_ctx* ctx, int64_t gx0, int64_t gy0);
+/* Moves and/or resizes the window to wg x wg global nodes anchored at (gx0, gy0), keeping the
+ * persistent local-node fields (isObstacle, risk) of the area both windows cover -- the reference
+ * subdivides on demand and never forgets a local node (L.cpp:150-156, G.cpp:36).  Deviation,
+ * local total cost and state start over (they are reset per propagation anyway, L.cpp:589-599).
+ * Creates the window if there is none. */
+int dymu_local_reshape(dymu_ctx* ctx, uint32_t wg, int64_t gx0, int64_t gy0); /* clears the window */
 int dymu_local_info(const dymu_ctx* ctx, int64_t* gx0, int64_t* gy0, uint32_t* wg, uint32_t* r);
 /* rectangle of the local window in window-local cell coordinates */
 int dymu_local_read_rect(dymu_ctx* ctx, int lplane, uint32_t x0, uint32_t y0, uint32_t w,

@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     };
     uint32_t phase = 0;
     unsigned long long n_tiles = 0, n_visits = 0, n_deferred = 0, n_inner = 0;
+    uint32_t n_written = 0;  // cells this thread stored back to the plane
 #ifdef DYMU_FIM_PROFILE
     long long pc_fetch = 0, pc_load = 0, pc_sweep = 0, pc_store = 0, pc_barrier = 0, pc_t = clock64();
 #define PC_MARK(acc) { long long now__ = clock64(); acc += now__ - pc_t; pc_t = now__; }
@@ -516,6 +517,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 double v = Ts[(y + 1) * P + x + 1];
                 if (v != told[k])
                 {
+                    n_written++;
                     __stcg(&Tg[(size_t)y * p.pitch + x], v);
                     if (MODE == 0)
                     {
@@ -596,6 +598,10 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 
     // ---- statistics
     if (lane == 0 && n_visits) atomicAdd(&p.stats[1], n_visits);
+    {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, n_written);
+        if (lane == 0 && w) atomicAdd(&p.stats[6], (unsigned long long)w);
+    }
     if (tid == 0)
     {
         if (n_tiles) atomicAdd(&p.stats[0], n_tiles);
@@ -976,6 +982,7 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
         stats->tiles_deferred = h[4];
         stats->inner_iterations = h[5];
         stats->goal_obstacle = (uint32_t)h[15];
+        stats->cells_written = h[6];
         DYMU_CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev1, ctx->ev2));
     }
     w->rot = (int)((prm.outer0 + h[2]) % 3);
@@ -1296,6 +1303,7 @@ static int solve_streamed(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint3
         stats->cell_updates += rest.cell_updates;
         stats->tiles_deferred += rest.tiles_deferred;
         stats->inner_iterations += rest.inner_iterations;
+        stats->cells_written += rest.cells_written;
         stats->kernel_ms += rest.kernel_ms;
     }
     ctx->solved = (rc == DYMU_OK);

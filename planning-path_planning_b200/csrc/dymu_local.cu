@@ -933,17 +933,8 @@ LocalView make_view(const dymu_ctx* ctx)
 
 static dymu_local* extra_of(dymu_ctx* ctx) { return &ctx->loc; }
 
-void dymu_internal_local_free(dymu_ctx* ctx)
-{
-    dymu_local& l = ctx->loc;
-    if (!l.allocated) return;
-    dymu_internal_fim_free(&l.work);
-    void* ptrs[] = {l.risk, l.dev, l.ltot, l.crisk, l.obst, l.state, l.nb_idx, l.first, l.prop,
-                    l.entered};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
-    memset(&l, 0, sizeof(l));
-}
+static void local_release(dymu_local& l);
+void dymu_internal_local_free(dymu_ctx* ctx) { local_release(ctx->loc); }
 
 static int local_clear(dymu_ctx* ctx)
 {
@@ -960,18 +951,14 @@ static int local_clear(dymu_ctx* ctx)
     return DYMU_OK;
 }
 
-extern "C" {
-
-int dymu_local_create(dymu_ctx* ctx, uint32_t wg)
+// Allocates the planes of a wg x wg window into `l` (which must not own memory) and clears them.
+static int local_alloc(dymu_ctx* ctx, dymu_local& l, uint32_t wg)
 {
-    DYMU_GUARD(ctx);
-    CallTrace call_trace(__func__);
-    if (!ctx || wg < 3) return DYMU_ERR_ARG;
-    dymu_internal_local_free(ctx);
-    dymu_local& l = ctx->loc;
+    memset(&l, 0, sizeof(l));
     l.wg = wg;
     l.r = (uint32_t)(ctx->gres / ctx->lres);  // res_ratio, G.cpp:49
     if (l.r < 1) DYMU_FAIL(ctx, DYMU_ERR_ARG, "local_res must not exceed global_res");
+    if ((uint64_t)wg * l.r > 65535u) DYMU_FAIL(ctx, DYMU_ERR_ARG, "local window of %u nodes is too large", wg);
     l.w = wg * l.r;
     uint32_t tile = ctx->tile;
     l.pitch = dymu_div_up(l.w, tile) * tile;
@@ -983,14 +970,49 @@ int dymu_local_create(dymu_ctx* ctx, uint32_t wg)
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.state, n));
     l.nb_cap = l.w * l.w;
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.nb_idx, (size_t)l.nb_cap * sizeof(uint32_t)));
-    dymu_local* e = &l;
-    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&e->first, (size_t)l.w * l.w * sizeof(uint32_t)));
-    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&e->prop, (size_t)l.nb_cap * sizeof(uint32_t)));
-    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&e->entered, (size_t)wg * wg));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(l.nb_idx, 0, (size_t)l.nb_cap * sizeof(uint32_t), ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.first, (size_t)l.w * l.w * sizeof(uint32_t)));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.prop, (size_t)l.nb_cap * sizeof(uint32_t)));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.entered, (size_t)wg * wg));
     uint32_t nt = l.pitch / tile;
     DYMU_TRY(dymu_internal_fim_alloc(ctx, &l.work, (size_t)nt * nt));
     l.allocated = true;
-    l.gx0 = l.gy0 = 0;
+    return DYMU_OK;
+}
+
+static void local_release(dymu_local& l)
+{
+    if (!l.allocated) return;
+    dymu_internal_fim_free(&l.work);
+    void* ptrs[] = {l.risk, l.dev, l.ltot, l.crisk, l.obst, l.state, l.nb_idx, l.first, l.prop, l.entered};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    memset(&l, 0, sizeof(l));
+}
+
+// deviation / total cost / state of every window cell back to "never propagated" (what the
+// reference's per-propagation reset of local_propagated_nodes, L.cpp:589-599, leaves behind)
+static int local_reset_wave(dymu_ctx* ctx)
+{
+    dymu_local& l = ctx->loc;
+    size_t n = (size_t)l.pitch * l.rows;
+    DYMU_TRY(dymu_internal_fill(ctx, l.dev, 1.0 / 0.0, n));
+    DYMU_TRY(dymu_internal_fill(ctx, l.ltot, 1.0 / 0.0, n));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(l.state, 0, n, ctx->stream));
+    l.prop_count = 0;
+    return DYMU_OK;
+}
+
+extern "C" {
+
+int dymu_local_create(dymu_ctx* ctx, uint32_t wg)
+{
+    DYMU_GUARD(ctx);
+    CallTrace call_trace(__func__);
+    if (!ctx || wg < 3) return DYMU_ERR_ARG;
+    dymu_internal_local_free(ctx);
+    DYMU_TRY(local_alloc(ctx, ctx->loc, wg));
+    ctx->loc.gx0 = ctx->loc.gy0 = 0;
     return local_clear(ctx);
 }
 
@@ -1002,6 +1024,59 @@ int dymu_local_anchor(dymu_ctx* ctx, int64_t gx0, int64_t gy0)
     ctx->loc.gx0 = gx0;
     ctx->loc.gy0 = gy0;
     return local_clear(ctx);
+}
+
+int dymu_local_reshape(dymu_ctx* ctx, uint32_t wg, int64_t gx0, int64_t gy0)
+{
+    DYMU_GUARD(ctx);
+    CallTrace call_trace(__func__);
+    if (!ctx || wg < 3) return DYMU_ERR_ARG;
+    if (!ctx->loc.allocated)
+    {
+        DYMU_TRY(local_alloc(ctx, ctx->loc, wg));
+        ctx->loc.gx0 = gx0;
+        ctx->loc.gy0 = gy0;
+        return local_clear(ctx);
+    }
+    dymu_local old = ctx->loc;  // keeps the device pointers of the current window
+    dymu_local fresh;
+    int rc = local_alloc(ctx, fresh, wg);
+    if (rc != DYMU_OK)
+    {
+        local_release(fresh);
+        return rc;
+    }
+    fresh.gx0 = gx0;
+    fresh.gy0 = gy0;
+    ctx->loc = fresh;
+    rc = local_clear(ctx);
+    // the persistent local-node fields -- isObstacle and risk (the reference never forgets a
+    // local node, L.cpp:150-156 and the empty destructor G.cpp:36) -- move with the overlap
+    const int64_t r = old.r;
+    const int64_t ox0 = old.gx0 * r, oy0 = old.gy0 * r, nx0 = gx0 * r, ny0 = gy0 * r;
+    const int64_t x0 = std::max(ox0, nx0), y0 = std::max(oy0, ny0);
+    const int64_t x1 = std::min(ox0 + (int64_t)old.w, nx0 + (int64_t)fresh.w);
+    const int64_t y1 = std::min(oy0 + (int64_t)old.w, ny0 + (int64_t)fresh.w);
+    if (rc == DYMU_OK && x1 > x0 && y1 > y0)
+    {
+        const size_t so = (size_t)(y0 - oy0) * old.pitch + (size_t)(x0 - ox0);
+        const size_t dn = (size_t)(y0 - ny0) * fresh.pitch + (size_t)(x0 - nx0);
+        const size_t cw = (size_t)(x1 - x0), ch = (size_t)(y1 - y0);
+        cudaError_t e1 = cudaMemcpy2DAsync(fresh.risk + dn, fresh.pitch * sizeof(double), old.risk + so,
+                                           old.pitch * sizeof(double), cw * sizeof(double), ch,
+                                           cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaError_t e2 = cudaMemcpy2DAsync(fresh.obst + dn, fresh.pitch, old.obst + so, old.pitch, cw, ch,
+                                           cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess)
+        {
+            snprintf(ctx->err, sizeof(ctx->err), "local window reshape: %s",
+                     cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            rc = DYMU_ERR_CUDA;
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    local_release(old);
+    return rc;
 }
 
 int dymu_local_info(const dymu_ctx* ctx, int64_t* gx0, int64_t* gy0, uint32_t* wg, uint32_t* r)
@@ -1223,6 +1298,14 @@ int dymu_local_propagate(dymu_ctx* ctx, int approach, double start_x, double sta
     *status = (uint32_t)h[1];
     if (n_closed) *n_closed = (uint64_t)h[2];
     e->prop_count = (uint32_t)h[3];
+    if (h[1] == DYMU_LOCAL_WINDOW_EXCEEDED)
+    {
+        // the march stopped in the middle of a pop: lanes may already have lowered deviations of
+        // cells that were never pushed, so the propagated-node list does not cover what was
+        // touched.  Put the whole window back to "never propagated"; the caller grows the window
+        // and marches again.
+        DYMU_TRY(local_reset_wave(ctx));
+    }
     return DYMU_OK;
 }
 

@@ -28,7 +28,8 @@ class SolveStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_uint32), ("converged", C.c_uint32),
                 ("tile_activations", C.c_uint64), ("cell_updates", C.c_uint64),
                 ("cells_reached", C.c_uint64), ("tiles_deferred", C.c_uint64), ("inner_iterations", C.c_uint64), ("kernel_ms", C.c_float), ("reset_ms", C.c_float),
-                ("goal_obstacle", C.c_uint32), ("reserved_", C.c_uint32)]
+                ("goal_obstacle", C.c_uint32), ("reserved_", C.c_uint32),
+                ("cells_written", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

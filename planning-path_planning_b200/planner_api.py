@@ -169,7 +169,7 @@ class Planner:
         return bool(self._l.dymu_planner_compute_entire_total_cost_map(self._h))
 
     def _path(self, fn, *args):
-        cap = 4096
+        cap = 1 << 15   # a second call would compute the path again
         while True:
             buf = np.empty((cap, 4), dtype=np.float64)
             n = fn(self._h, *args, _ptr(buf), cap)

@@ -142,7 +142,8 @@ class DyMuPathPlanner
     // obstacles ingested but not yet expanded (local_expandable_obstacles, DyMu.hpp:452)
     bool pending_risk;
     uint local_window_nodes;
-    bool local_ready;
+    bool local_ready;    // the window is placed (anchored) and holds the local layer
+    bool local_created;  // the window is allocated
     long local_agent_cell;
     // node views handed out by getGlobalNode / getLocalNode
     std::map<unsigned long long, globalNode> global_views;
@@ -155,7 +156,8 @@ class DyMuPathPlanner
     bool deviceOk(int rc, const char* what);
     long nearestIndex(double x, double y) const;  // getNearestGlobalNode as j*NX+i or -1
     void subdivideIndex(long g);
-    bool ensureLocalWindow(double x, double y, double half_x, double half_y, bool may_reanchor);
+    bool ensureLocalWindow(double x, double y, double half_x, double half_y, bool may_grow);
+    bool growLocalWindow(long lo_x, long hi_x, long lo_y, long hi_y);
     bool readNode(uint i, uint j, globalNode& out);
     void markEntered();
     long localPropagationCell(base::Waypoint wInit, base::Waypoint wOvertake);

@@ -52,6 +52,7 @@ DyMuPathPlanner::DyMuPathPlanner(double risk_distance,
       pending_risk(false),
       local_window_nodes(64),
       local_ready(false),
+      local_created(false),
       local_agent_cell(-1)
 {
     global_goal = NULL;
@@ -118,6 +119,9 @@ bool DyMuPathPlanner::initGlobalLayer(double globalres,
     closed_threshold = kInf;
     pending_risk = false;
     local_ready = false;
+    // the local window is allocated up front (the reference builds its whole node graph here): the
+    // first repair does not pay for cudaMalloc
+    local_created = deviceOk(dymu_local_create(dev, local_window_nodes), "local window");
     return true;
 }
 

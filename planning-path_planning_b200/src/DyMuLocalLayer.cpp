@@ -15,6 +15,8 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 
@@ -25,6 +27,30 @@ using namespace PathPlanning_lib;
 namespace
 {
 const double kInf = std::numeric_limits<double>::infinity();
+
+// DYMU_TIMING=1: wall time per stage of the local layer on stderr (developer aid)
+struct Lap
+{
+    const char* name;
+    double t0;
+    static bool on()
+    {
+        static int v = -1;
+        if (v < 0) v = getenv("DYMU_TIMING") ? 1 : 0;
+        return v == 1;
+    }
+    static double now()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit Lap(const char* n) : name(n), t0(on() ? now() : 0.0) {}
+    ~Lap()
+    {
+        if (on()) fprintf(stderr, "[dymu timing] %-28s %8.3f ms\n", name, now() - t0);
+    }
+};
 
 double dist2(const base::Waypoint& a, const base::Waypoint& b)
 {
@@ -54,35 +80,70 @@ void DyMuPathPlanner::subdivideGlobalNode(globalNode* gNode)
 }
 
 // Makes sure the device window exists and covers the rectangle centred on (x, y) with the
-// given half extents (metres) plus a margin for the risk band and the local wave.  The
-// window is re-anchored (and thereby cleared) only when the rectangle does not fit.
+// given half extents (metres) plus a margin for the risk band and the local wave.  The reference's
+// local layer is unbounded and never forgets (L.cpp:150-156, G.cpp:36); the device window follows
+// it by growing to the union of what it holds and what is asked for (obstacles and risk move
+// along, dymu_local_reshape).  Only beyond kMaxLocalWindow nodes it slides instead, keeping the
+// overlap and dropping what falls outside, with a warning.
 bool DyMuPathPlanner::ensureLocalWindow(double x, double y, double half_x, double half_y,
-                                        bool may_reanchor)
+                                        bool may_grow)
 {
     if (!dev) return false;
+    double margin = 3.0 * global_res;
+    long lo_x = (long)floor((x - half_x - margin) / global_res), hi_x = (long)ceil((x + half_x + margin) / global_res);
+    long lo_y = (long)floor((y - half_y - margin) / global_res), hi_y = (long)ceil((y + half_y + margin) / global_res);
     if (!local_ready)
     {
-        if (!deviceOk(dymu_local_create(dev, local_window_nodes), "local window")) return false;
+        long need = std::max(hi_x - lo_x, hi_y - lo_y);
+        long wg = std::max((long)local_window_nodes, need);
+        int64_t gx0 = (lo_x + hi_x) / 2 - wg / 2, gy0 = (lo_y + hi_y) / 2 - wg / 2;
+        // the window allocated by initGlobalLayer is empty: placing it is a clear, not a copy
+        if (local_created && wg == (long)local_window_nodes)
+        {
+            if (!deviceOk(dymu_local_anchor(dev, gx0, gy0), "local window")) return false;
+        }
+        else if (!deviceOk(dymu_local_reshape(dev, (uint32_t)wg, gx0, gy0), "local window"))
+            return false;
+        local_created = true;
         local_ready = true;
-        int64_t gx0 = (int64_t)floor(x / global_res) - (int64_t)local_window_nodes / 2;
-        int64_t gy0 = (int64_t)floor(y / global_res) - (int64_t)local_window_nodes / 2;
-        return deviceOk(dymu_local_anchor(dev, gx0, gy0), "local window");
+        return true;
     }
     int64_t gx0, gy0;
     uint32_t wg, r;
     dymu_local_info(dev, &gx0, &gy0, &wg, &r);
-    double margin = 3.0 * global_res;
-    double lo_x = (x - half_x - margin) / global_res, hi_x = (x + half_x + margin) / global_res;
-    double lo_y = (y - half_y - margin) / global_res, hi_y = (y + half_y + margin) / global_res;
-    bool fits = lo_x >= (double)gx0 && hi_x <= (double)(gx0 + wg) && lo_y >= (double)gy0
-                && hi_y <= (double)(gy0 + wg);
+    bool fits = lo_x >= (long)gx0 && hi_x <= (long)(gx0 + wg) && lo_y >= (long)gy0 && hi_y <= (long)(gy0 + wg);
     if (fits) return true;
-    if (!may_reanchor) return false;
-    LOG_WARN_S << "PLANNER (B200): re-anchoring the local window; earlier local obstacles are dropped";
-    pending_risk = false;
-    int64_t nx0 = (int64_t)floor(x / global_res) - (int64_t)wg / 2;
-    int64_t ny0 = (int64_t)floor(y / global_res) - (int64_t)wg / 2;
-    return deviceOk(dymu_local_anchor(dev, nx0, ny0), "local window");
+    if (!may_grow) return false;
+    return growLocalWindow(lo_x, hi_x, lo_y, hi_y);
+}
+
+// New window = union of the current one and [lo, hi) (global nodes) with a quarter of slack.
+bool DyMuPathPlanner::growLocalWindow(long lo_x, long hi_x, long lo_y, long hi_y)
+{
+    const long kMaxLocalWindow = 512;  // nodes per edge; whole-window kernels stay cheap below this
+    int64_t gx0, gy0;
+    uint32_t wg, r;
+    dymu_local_info(dev, &gx0, &gy0, &wg, &r);
+    long ux0 = std::min(lo_x, (long)gx0), ux1 = std::max(hi_x, (long)(gx0 + wg));
+    long uy0 = std::min(lo_y, (long)gy0), uy1 = std::max(hi_y, (long)(gy0 + wg));
+    long need = std::max(ux1 - ux0, uy1 - uy0);
+    long nwg = need + need / 4;
+    nwg = (nwg + 7) / 8 * 8;
+    int64_t nx0, ny0;
+    if (nwg <= kMaxLocalWindow && (uint64_t)nwg * r <= 65535u)
+    {
+        nx0 = (ux0 + ux1) / 2 - nwg / 2;
+        ny0 = (uy0 + uy1) / 2 - nwg / 2;
+    }
+    else
+    {
+        // slide: same size (or what the request needs), centred on the request
+        nwg = std::max((long)wg, std::max(hi_x - lo_x, hi_y - lo_y));
+        nx0 = (lo_x + hi_x) / 2 - nwg / 2;
+        ny0 = (lo_y + hi_y) / 2 - nwg / 2;
+        LOG_WARN_S << "PLANNER (B200): local window limit reached; local obstacles outside the new window are dropped";
+    }
+    return deviceOk(dymu_local_reshape(dev, (uint32_t)nwg, nx0, ny0), "local window");
 }
 
 // localNode::global_pose of a window cell, L.cpp:35-40
@@ -114,7 +175,7 @@ localNode* DyMuPathPlanner::getLocalNode(base::Waypoint wPos)
     long g = nearestIndex(wPos.position[0], wPos.position[1]);
     if (g < 0 || !dev) return NULL;
     subdivideIndex(g);
-    if (!ensureLocalWindow(wPos.position[0], wPos.position[1], 0.0, 0.0, false)) return NULL;
+    if (!ensureLocalWindow(wPos.position[0], wPos.position[1], 0.0, 0.0, true)) return NULL;
     int64_t cell = -1;
     if (!deviceOk(dymu_local_cell_of(dev, wPos.position[0], wPos.position[1], &cell), "getLocalNode"))
         return NULL;
@@ -167,9 +228,13 @@ bool DyMuPathPlanner::computeLocalPlanning(base::Waypoint wPos,
     for (uint j = a; j < b; j++)
         for (uint i = c; i < d; i++) subdivideIndex((long)j * num_nodes_X + i);
 
-    if (!ensureLocalWindow(wPos.position[0], wPos.position[1], res * (double)width / 2,
-                           res * (double)height / 2, true))
-        return false;
+    {
+        Lap lap("ensureLocalWindow");
+        if (!ensureLocalWindow(wPos.position[0], wPos.position[1], res * (double)width / 2,
+                               res * (double)height / 2, true))
+            return false;
+    }
+    Lap lap_all("computeLocalPlanning (rest)");
 
     // getLocalNode(pos) subdivides the nearest node of every in-map pixel (L.cpp:246)
     double offsetX = wPos.position[0] - res * (double)width / 2;
@@ -190,12 +255,17 @@ bool DyMuPathPlanner::computeLocalPlanning(base::Waypoint wPos,
     // obstacle / risk mask on the device; new obstacle cells come back in raster order
     std::vector<uint32_t> new_cells((size_t)width * height);
     uint32_t n_new = 0;
+    Lap* lap_ing = new Lap("ingest");
     if (!deviceOk(dymu_local_ingest(dev, traversabilityMap.image.data(), width, height,
                                     traversabilityMap.getRowSize(), traversabilityMap.getPixelSize(),
                                     res, wPos.position[0], wPos.position[1], new_cells.data(),
                                     (uint32_t)new_cells.size(), &n_new),
                   "computeLocalPlanning"))
+    {
+        delete lap_ing;
         return false;
+    }
+    delete lap_ing;
 
     uint minIndex = current_path.size(), maxIndex = 0;
     bool pathBlocked = false;
@@ -276,10 +346,20 @@ bool DyMuPathPlanner::computeLocalPlanning(base::Waypoint wPos,
     if ((pathBlocked) && (maxIndex > minIndex))
     {
         base::Time tInit = base::Time::now();
-        expandRisk();
+        {
+            Lap lap("expandRisk");
+            expandRisk();
+        }
         trajectory.clear();
-        reconnecting_index = repairPath(wPos, maxIndex);
-        if (repairing_approach == SWEEPING) evaluatePath(reconnecting_index);
+        {
+            Lap lap("repairPath");
+            reconnecting_index = repairPath(wPos, maxIndex);
+        }
+        if (repairing_approach == SWEEPING)
+        {
+            Lap lap("evaluatePath");
+            evaluatePath(reconnecting_index);
+        }
         trajectory = current_path;
         localTime = base::Time::now() - tInit;
         return true;
@@ -356,18 +436,30 @@ long DyMuPathPlanner::localPropagationCell(base::Waypoint wayp_start, base::Wayp
     // getTotalCost(Waypoint) subtracts the offset from an already offset-free waypoint
     // (L.cpp:583 -> G.cpp:862-863); reproduced as is
     double Tovertake = getTotalCost(wOvertake);
-    if (!ensureLocalWindow(wayp_start.position[0], wayp_start.position[1], 0.0, 0.0, false)) return -1;
+    if (!ensureLocalWindow(wayp_start.position[0], wayp_start.position[1], 0.0, 0.0, true)) return -1;
     subdivideIndex(nearestIndex(wayp_start.position[0], wayp_start.position[1]));  // getLocalNode(wayp_start)
     if (repairing_approach == CONSERVATIVE)
         subdivideIndex(nearestIndex(wOvertake.position[0], wOvertake.position[1]));  // getLocalNode(wOvertake)
     int64_t end_cell = -1;
     uint32_t status = 0;
     uint64_t closed = 0;
-    if (!deviceOk(dymu_local_propagate(dev, repairing_approach == SWEEPING ? 1 : 0, wayp_start.position[0],
-                                       wayp_start.position[1], wOvertake.position[0], wOvertake.position[1],
-                                       Tovertake, risk_ratio, &end_cell, &status, &closed),
-                  "computeLocalPropagation"))
-        return -1;
+    for (int attempt = 0;; ++attempt)
+    {
+        if (!deviceOk(dymu_local_propagate(dev, repairing_approach == SWEEPING ? 1 : 0, wayp_start.position[0],
+                                           wayp_start.position[1], wOvertake.position[0], wOvertake.position[1],
+                                           Tovertake, risk_ratio, &end_cell, &status, &closed),
+                      "computeLocalPropagation"))
+            return -1;
+        if (status != DYMU_LOCAL_WINDOW_EXCEEDED || attempt >= 4) break;
+        // the wave reached the window border (the reference's layer has none): double the window
+        // around its centre -- obstacles and risk move along -- and march again
+        int64_t gx0, gy0;
+        uint32_t wg, r;
+        dymu_local_info(dev, &gx0, &gy0, &wg, &r);
+        long half = (long)wg / 2;
+        if (!growLocalWindow((long)gx0 - half, (long)(gx0 + wg) + half, (long)gy0 - half, (long)(gy0 + wg) + half))
+            return -1;
+    }
     markEntered();
     int64_t c = -1;
     dymu_local_cell_of(dev, wayp_start.position[0], wayp_start.position[1], &c);
@@ -474,7 +566,11 @@ int DyMuPathPlanner::repairPath(base::Waypoint wayp_start, uint index)
         return -1;
     }
 
-    long lSet = localPropagationCell(wayp_start, current_path[index]);
+    long lSet;
+    {
+        Lap lap("  localPropagationCell");
+        lSet = localPropagationCell(wayp_start, current_path[index]);
+    }
     if (lSet < 0)
     {
         LOG_WARN_S << "Repairing aborted, the robot is in obstacle area";
@@ -496,23 +592,49 @@ int DyMuPathPlanner::repairPath(base::Waypoint wayp_start, uint index)
     for (uint k = closest_index; k < index; k++)
         original_distance += dist2(current_path[k + 1], current_path[k]);
 
-    std::vector<base::Waypoint> localPath = localPathFromCell(lSet, wayp_start);
+    std::vector<base::Waypoint> localPath;
+    {
+        Lap lap("  localPathFromCell");
+        localPath = localPathFromCell(lSet, wayp_start);
+    }
     double lgx, lgy;
     localCellPose(lSet, lgx, lgy);
     if (localPath.size() > 1)
     {
         for (uint k = 0; k < localPath.size() - 1; k++) new_distance += dist2(localPath[k + 1], localPath[k]);
         // trafficability feedback on the traversed global nodes, L.cpp:388-394
-        for (uint k = closest_index; k < index; k++)
         {
-            long g = nearestIndex(current_path[k].position[0], current_path[k].position[1]);
-            if (g < 0) continue;
-            uint32_t gi = (uint32_t)(g % num_nodes_X), gj = (uint32_t)(g / num_nodes_X);
-            double t = 1.0;
-            if (!deviceOk(dymu_read_rect(dev, DYMU_PLANE_TRAFFICABILITY, gi, gj, 1, 1, &t), "trafficability"))
-                break;
-            t = std::min(original_distance / new_distance, t);
-            deviceOk(dymu_write_rect(dev, DYMU_PLANE_TRAFFICABILITY, gi, gj, 1, 1, &t), "trafficability");
+            Lap lap_tr("  trafficability feedback");
+            // one read and one write of the bounding rectangle instead of a round trip per waypoint
+            std::vector<long> nodes;
+            long lo_i = num_nodes_X, hi_i = -1, lo_j = num_nodes_Y, hi_j = -1;
+            for (uint k = closest_index; k < index; k++)
+            {
+                long g = nearestIndex(current_path[k].position[0], current_path[k].position[1]);
+                if (g < 0) continue;
+                nodes.push_back(g);
+                long gi = g % num_nodes_X, gj = g / num_nodes_X;
+                lo_i = std::min(lo_i, gi); hi_i = std::max(hi_i, gi);
+                lo_j = std::min(lo_j, gj); hi_j = std::max(hi_j, gj);
+            }
+            if (!nodes.empty())
+            {
+                uint32_t rw = (uint32_t)(hi_i - lo_i + 1), rh = (uint32_t)(hi_j - lo_j + 1);
+                std::vector<double> tr((size_t)rw * rh);
+                if (deviceOk(dymu_read_rect(dev, DYMU_PLANE_TRAFFICABILITY, (uint32_t)lo_i, (uint32_t)lo_j, rw, rh,
+                                            tr.data()),
+                             "trafficability"))
+                {
+                    for (size_t q = 0; q < nodes.size(); ++q)
+                    {
+                        double& t = tr[(size_t)(nodes[q] / num_nodes_X - lo_j) * rw + (nodes[q] % num_nodes_X - lo_i)];
+                        t = std::min(original_distance / new_distance, t);
+                    }
+                    deviceOk(dymu_write_rect(dev, DYMU_PLANE_TRAFFICABILITY, (uint32_t)lo_i, (uint32_t)lo_j, rw, rh,
+                                             tr.data()),
+                             "trafficability");
+                }
+            }
         }
         if (repairing_approach == CONSERVATIVE)
         {
@@ -526,7 +648,10 @@ int DyMuPathPlanner::repairPath(base::Waypoint wayp_start, uint index)
             base::Waypoint newWaypoint;
             newWaypoint.position[0] = lgx;
             newWaypoint.position[1] = lgy;
-            computeGlobalPath(newWaypoint);
+            {
+                Lap lap("  computeGlobalPath");
+                computeGlobalPath(newWaypoint);
+            }
             localPath.pop_back();
             current_path.insert(current_path.begin(), localPath.begin(), localPath.end());
             return localPath.size();

@@ -253,3 +253,51 @@ def test_streamed_cost_map_invalid_goal(pkg):
     assert p.setCostMapFlat(bad)
     assert not p.computeEntireTotalCostMap()
     assert not p.computeEntireTotalCostMap()     # and again through the settled (non-streamed) path
+
+
+def _repair_at(p, syn, path, k0, seed):
+    """A frame centred on path[k0] with an obstacle disc on the path 1.2 m ahead (+2 random discs)."""
+    c = path[k0, :2]
+    d = path[min(k0 + 12, len(path) - 2), :2]
+    rng = np.random.default_rng(seed)
+    discs = [(d[0], d[1], 0.8)] + [(c[0] + rng.uniform(-4, 4), c[1] + rng.uniform(-4, 4), rng.uniform(0.2, 0.5))
+                                   for _ in range(2)]
+    img = syn.obstacle_frame(120, 120, 0.1, c, discs)
+    repaired, traj, _ = p.computeLocalPlanning(c[0], c[1], img, 0.1)
+    return dict(repaired=repaired, traj=traj, centre=c, risk=p.getRiskMatrix(c[0], c[1]),
+                deviation=p.getDeviationMatrix(c[0], c[1]), reconnecting_index=p.getReconnectingIndex())
+
+
+@pytest.mark.parametrize("approach", [1, 0])
+def test_local_window_grows_and_keeps_obstacles(pkg, ref_lib, approach, monkeypatch):
+    """The reference's local layer is unbounded and never forgets (L.cpp:150-156, G.cpp:36).  With a
+    device window of only 16 global nodes the first frame does not fit (the window is re-created
+    larger), the local wave runs into its border (it is doubled and the march repeated), and a
+    second repair 40 m further along the path makes it grow to the union -- the obstacles and the
+    risk of the first repair must still be there, as in the reference."""
+    monkeypatch.setenv("DYMU_LOCAL_WINDOW", "16")
+    n, syn = 300, pkg.synthetic
+    res = []
+    for p in _pair(pkg, ref_lib, approach, n, n):
+        g = sc.global_scenario(p, syn, n, n, seed=5, entire=True)
+        r1 = _repair_at(p, syn, g["path"], 0, seed=21)
+        path = p.current_path
+        k1 = int(np.argmax(np.hypot(path[:, 0] - r1["centre"][0], path[:, 1] - r1["centre"][1]) > 40.0))
+        assert k1 > 0
+        r2 = _repair_at(p, syn, path, k1, seed=22)
+        back = p.getRiskMatrix(r1["centre"][0], r1["centre"][1])      # first site, after the second repair
+        res.append((r1, r2, back, p.node_field(6), p.getHazardDensityMatrix(), p.getTrafficabilityMatrix()))
+    (a1, a2, aback, ha, hza, tra), (b1, b2, bback, hb, hzb, trb) = res
+    for a, b in ((a1, b1), (a2, b2)):
+        assert a["repaired"] and b["repaired"]
+        assert np.array_equal(a["risk"] > 0, b["risk"] > 0) and np.array_equal(a["risk"] == 1.0, b["risk"] == 1.0)
+        assert np.max(np.abs(a["risk"] - b["risk"])) <= 1e-12
+        assert np.array_equal(a["deviation"] < 0, b["deviation"] < 0)
+        assert rel_err(b["deviation"], a["deviation"]) <= TOL_PLANE
+        assert a["reconnecting_index"] == b["reconnecting_index"]
+        assert a["traj"].shape == b["traj"].shape
+        assert np.max(np.abs(a["traj"][:, :2] - b["traj"][:, :2])) <= TOL_WP
+    assert (aback == 1.0).any(), "the first site's obstacles are inside the tap"
+    assert np.array_equal(aback > 0, bback > 0) and np.max(np.abs(aback - bback)) <= 1e-12
+    assert np.array_equal(ha, hb), "hasLocalMap"
+    assert np.max(np.abs(hza - hzb)) <= 1e-12 and np.max(np.abs(tra - trb)) <= 1e-9
