@@ -240,6 +240,41 @@ int dymu_extract_global_path_batch(dymu_ctx* ctx, uint32_t n, const uint32_t* sl
                                    const double* xy0, double tau, const uint32_t* goal_ij,
                                    double* out, uint32_t cap, uint32_t* n_out, int* status);
 
+/* ---- several GPUs behind one call ------------------------------- */
+/* Batches of independent goal queries: context k (its own GPU, its own copy of the cost map,
+ * dymu_reserve_slots goals per launch) gets the k-th contiguous block of the n_goals queries; one
+ * host thread per context, no data-path exchange.  Per query: computeEntireTotalCostMap
+ * (G.cpp:443-468) and, if `paths` is given, the descent from (start_xy[2q], start_xy[2q+1])
+ * (G.cpp:615-714) into paths + q*cap*5 (format of dymu_extract_global_path), path_len[q],
+ * path_status[q].  ms_per_ctx (optional): host wall time of each context's share. */
+int dymu_batch_solve(dymu_ctx** ctxs, uint32_t n_ctx, uint32_t n_goals, const uint32_t* goal_i,
+                     const uint32_t* goal_j, const double* start_xy, double tau, double* paths,
+                     uint32_t cap, uint32_t* path_len, int32_t* path_status, float* ms_per_ctx);
+
+typedef struct dymu_dd_stats
+{
+    uint32_t rounds;            /* exchange rounds */
+    uint32_t converged;
+    float wall_ms;              /* host wall clock of the whole solve */
+    float max_kernel_ms;        /* solver kernel time of the busiest strip */
+    float sum_kernel_ms;        /* ... summed over the strips */
+    uint32_t reserved_;
+    uint64_t tile_activations;  /* summed over the strips */
+    uint64_t cell_updates;
+} dymu_dd_stats;
+
+/* One grid cut into n row strips, strip k on context k: global rows [cuts[k], cuts[k+1]) plus
+ * one ghost row per interior side (cost 0 there), i.e. ctxs[k] has cuts[k+1]-cuts[k] (+1) (+1)
+ * rows, the common width, and its cost map set (dymu_set_cost_map on the strip's rows; interior
+ * cuts on multiples of the 32-cell tile).  The goal is given in grid coordinates.  Every round a
+ * strip runs at most phases_per_round solver phases (0 = 32), then boundary rows travel GPU to
+ * GPU (cudaMemcpyPeerAsync) into the neighbours' ghost rows; computeEntireTotalCostMap
+ * (G.cpp:443-468) of the whole grid, same fixed point as the single-grid solve.  On return each
+ * strip's total-cost plane holds its rows (dymu_download_total_cost; row 0 is the ghost row for
+ * k > 0). */
+int dymu_dd_solve(dymu_ctx** ctxs, uint32_t n, const uint32_t* cuts, uint32_t goal_i, uint32_t goal_j,
+                  uint32_t phases_per_round, dymu_dd_stats* stats);
+
 /* ---- local layer --------------------------------------------------------------------- */
 /* The local layer (localNode, H.hpp:42-67) is a dense window of wg x wg global
  * nodes, r = (uint)(global_res/local_res) local cells per node edge, anchored at

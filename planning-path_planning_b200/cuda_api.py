@@ -24,6 +24,15 @@ _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
 
 
+class DdStats(C.Structure):
+    _fields_ = [("rounds", C.c_uint32), ("converged", C.c_uint32), ("wall_ms", C.c_float),
+                ("max_kernel_ms", C.c_float), ("sum_kernel_ms", C.c_float), ("reserved_", C.c_uint32),
+                ("tile_activations", C.c_uint64), ("cell_updates", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_"}
+
+
 class SolveStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_uint32), ("converged", C.c_uint32),
                 ("tile_activations", C.c_uint64), ("cell_updates", C.c_uint64),
@@ -59,6 +68,11 @@ _SIG = {
                                     C.c_uint32, _u8p]),
     "dymu_plane_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_size_t)]),
+    "dymu_dd_solve": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, _u32p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                C.POINTER(DdStats)]),
+    "dymu_batch_solve": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, _u32p, _u32p, _dp, C.c_double,
+                                   _dp, C.c_uint32, _u32p, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
+    "dymu_local_reshape": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int64, C.c_int64]),
     "dymu_set_cost_map_begin": (C.c_int, [C.c_void_p, _dp, C.c_size_t, C.c_uint32]),
     "dymu_set_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_size_t]),
     "dymu_compute_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp,
@@ -495,3 +509,56 @@ class DeviceLayer:
         c = C.c_int64()
         self._chk(self._l.dymu_local_cell_of(self._h, x, y, C.byref(c)))
         return c.value
+
+
+# ---- several contexts behind one call (include/dymu_cuda.h, "several GPUs behind one call") ----
+def _ctx_array(layers):
+    arr = (C.c_void_p * len(layers))()
+    for k, d in enumerate(layers):
+        arr[k] = d._h
+    return arr
+
+
+def dd_solve(layers, cuts, goal, phases_per_round=32):
+    """dymu_dd_solve: `layers[k]` is the DeviceLayer of strip k (own rows [cuts[k], cuts[k+1]) plus
+    ghost rows, cost map set), `goal` = (i, j) in grid coordinates.  Returns the statistics dict."""
+    lib = load_library()
+    c = np.ascontiguousarray(cuts, dtype=np.uint32)
+    if c.size != len(layers) + 1:
+        raise ValueError("cuts must hold len(layers) + 1 rows")
+    st = DdStats()
+    rc = lib.dymu_dd_solve(_ctx_array(layers), len(layers), c.ctypes.data_as(_u32p), int(goal[0]), int(goal[1]),
+                           int(phases_per_round), C.byref(st))
+    if rc != 0:
+        texts = [lib.dymu_last_error(d._h).decode() for d in layers]
+        raise DymuError(rc, "; ".join(t for t in texts if t))
+    return st.as_dict()
+
+
+def batch_solve(layers, goals, starts=None, tau=0.4, cap=1 << 14):
+    """dymu_batch_solve: the goal queries are dealt out over `layers` (one context per GPU, same cost
+    map, reserve_slots() goals per launch).  Returns (paths or None, per-context wall ms)."""
+    lib = load_library()
+    g = np.ascontiguousarray(goals, dtype=np.uint32).reshape(-1, 2)
+    gi, gj = np.ascontiguousarray(g[:, 0]), np.ascontiguousarray(g[:, 1])
+    n = g.shape[0]
+    ms = np.zeros(len(layers), dtype=np.float32)
+    if starts is None:
+        rc = lib.dymu_batch_solve(_ctx_array(layers), len(layers), n, gi.ctypes.data_as(_u32p),
+                                  gj.ctypes.data_as(_u32p), None, float(tau), None, 0, None, None,
+                                  ms.ctypes.data_as(C.POINTER(C.c_float)))
+        paths = None
+    else:
+        xy = np.ascontiguousarray(starts, dtype=np.float64).reshape(n, 2)
+        out = np.empty((n, cap, 5), dtype=np.float64)
+        ln = np.zeros(n, dtype=np.uint32)
+        stt = np.zeros(n, dtype=np.int32)
+        rc = lib.dymu_batch_solve(_ctx_array(layers), len(layers), n, gi.ctypes.data_as(_u32p),
+                                  gj.ctypes.data_as(_u32p), xy.ctypes.data_as(_dp), float(tau),
+                                  out.ctypes.data_as(_dp), int(cap), ln.ctypes.data_as(_u32p),
+                                  stt.ctypes.data_as(C.POINTER(C.c_int32)), ms.ctypes.data_as(C.POINTER(C.c_float)))
+        paths = [(out[q, :ln[q]].copy(), int(stt[q])) for q in range(n)]
+    if rc != 0:
+        texts = [lib.dymu_last_error(d._h).decode() for d in layers]
+        raise DymuError(rc, "; ".join(t for t in texts if t))
+    return paths, ms

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "dymu_cuda.h"
+#include "DyMuTiming.hpp"
 #include "dymu_planner_c.h"
 
 using namespace PathPlanning_lib;
@@ -458,10 +459,10 @@ bool DyMuPathPlanner::computeEntireTotalCostMap()
         return false;
     }
     closed_threshold = kInf;
-    startReadback();
     double heading = global_goal->pose.orientation;
     readNode(goal_i, goal_j, goal_view);
     goal_view.pose.orientation = heading;
+    startReadback();
     return true;
 }
 
@@ -491,8 +492,15 @@ std::vector<base::Waypoint> DyMuPathPlanner::getPath(base::Waypoint wPos)
 {
     wPos.position[0] -= global_offset[0];
     wPos.position[1] -= global_offset[1];
-    computeGlobalPath(wPos);
-    evaluatePath(0);
+    {
+        Lap lap("getPath: computeGlobalPath");
+        computeGlobalPath(wPos);
+    }
+    {
+        Lap lap("getPath: evaluatePath");
+        evaluatePath(0);
+    }
+    Lap lap("getPath: copy out");
     std::vector<base::Waypoint> output_path = current_path;
     for (size_t i = 0; i < output_path.size(); i++)
     {
@@ -514,15 +522,13 @@ bool DyMuPathPlanner::computeGlobalPath(base::Waypoint wPos)
     base::Waypoint sinkPoint;
     sinkPoint.position[0] = global_res * (double)goal_i;
     sinkPoint.position[1] = global_res * (double)goal_j;
-    globalNode g;
-    readNode(goal_i, goal_j, g);
-    sinkPoint.position[2] = g.elevation;
     sinkPoint.heading = global_goal ? global_goal->pose.orientation : 0.0;
 
     double tau = std::min(0.4, risk_distance);
     uint32_t cap = 1u << 16, n = 0;
     int status = 0;
     std::vector<double> buf;
+    Lap lap_x("  extract + convert");
     for (;;)
     {
         buf.resize((size_t)cap * 5);
@@ -554,6 +560,12 @@ bool DyMuPathPlanner::computeGlobalPath(base::Waypoint wPos)
         LOG_ERROR_S << "ERROR in trajectory";
         return false;
     }
+    // the goal's elevation is read after the descent: a small device-to-host copy queues behind a
+    // total-cost matrix delivery that may be in flight (setTotalCostMatrixTarget), and by now that
+    // copy has had the whole descent to finish
+    globalNode g;
+    readNode(goal_i, goal_j, g);
+    sinkPoint.position[2] = g.elevation;
     current_path.push_back(sinkPoint);
     return true;
 }

@@ -21,36 +21,13 @@
 #include <algorithm>
 
 #include "dymu_cuda.h"
+#include "DyMuTiming.hpp"
 
 using namespace PathPlanning_lib;
 
 namespace
 {
 const double kInf = std::numeric_limits<double>::infinity();
-
-// DYMU_TIMING=1: wall time per stage of the local layer on stderr (developer aid)
-struct Lap
-{
-    const char* name;
-    double t0;
-    static bool on()
-    {
-        static int v = -1;
-        if (v < 0) v = getenv("DYMU_TIMING") ? 1 : 0;
-        return v == 1;
-    }
-    static double now()
-    {
-        timespec ts;
-        clock_gettime(CLOCK_MONOTONIC, &ts);
-        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-    }
-    explicit Lap(const char* n) : name(n), t0(on() ? now() : 0.0) {}
-    ~Lap()
-    {
-        if (on()) fprintf(stderr, "[dymu timing] %-28s %8.3f ms\n", name, now() - t0);
-    }
-};
 
 double dist2(const base::Waypoint& a, const base::Waypoint& b)
 {

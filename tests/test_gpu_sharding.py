@@ -103,3 +103,104 @@ def test_pipelined_strips_equal_single_grid(pkg, k, phases):
     assert rounds >= 2
     assert np.array_equal(np.isinf(Tk), np.isinf(T1))
     assert rel_err(Tk, T1) <= 1e-12
+
+
+def _strip_layers(pkg, cost, k, devices):
+    """DeviceLayers of k row strips of `cost` (ghost rows = obstacles) + the cut rows."""
+    sh, api = pkg.sharding, pkg.cuda_api
+    ny, nx = cost.shape
+    layers, cuts = [], [0]
+    for r in range(k):
+        lay = sh.StripLayout(ny, k, r)
+        d = api.DeviceLayer(nx, lay.ny_local, 1.0, 0.1, device=devices[r % len(devices)])
+        d.set_cost_map(lay.local_cost(cost[lay.r0:lay.r1]))
+        layers.append((d, lay))
+        cuts.append(lay.r1)
+    return layers, cuts
+
+
+def _gather_strips(layers):
+    return np.vstack([d.download_total_cost()[lay.first_own:lay.last_own + 1] for d, lay in layers])
+
+
+@pytest.mark.parametrize("k,phases", [(2, 8), (3, 32), (5, 2)])
+def test_dd_solve_c_abi_on_one_device(pkg, k, phases):
+    """dymu_dd_solve with k strips that all live on one GPU (one host thread per strip, rows copied
+    device to device): same plane as the single-grid solve."""
+    api, syn = pkg.cuda_api, pkg.synthetic
+    ny, nx = 448, 352
+    cost = syn.smooth_cost_map(ny, nx, seed=23, obstacle_fraction=0.04)
+    goal = syn.free_interior_cell_near(cost <= 0, 120, 300)
+    whole = api.DeviceLayer(nx, ny)
+    whole.set_cost_map(cost)
+    whole.solve_total_cost([goal])
+    T1 = whole.download_total_cost()
+    layers, cuts = _strip_layers(pkg, cost, k, [0])
+    st = api.dd_solve([d for d, _ in layers], cuts, goal, phases)
+    assert st["converged"] and st["rounds"] >= 2
+    Tk = _gather_strips(layers)
+    assert np.array_equal(np.isinf(Tk), np.isinf(T1))
+    assert rel_err(Tk, T1) <= 1e-12
+    # a second solve on the same contexts (other goal) starts clean
+    goal2 = syn.free_interior_cell_near(cost <= 0, 300, 60)
+    whole.solve_total_cost([goal2])
+    api.dd_solve([d for d, _ in layers], cuts, goal2, phases)
+    assert rel_err(_gather_strips(layers), whole.download_total_cost()) <= 1e-12
+
+
+def test_dd_solve_c_abi_across_devices(pkg):
+    """The same with every strip on its own GPU (peer copies over NVLink); skipped below 2 GPUs.
+    16384^2 (BASELINE configs[4]) when the box has the memory for it, else 4096^2."""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs at least two GPUs")
+    api, syn = pkg.cuda_api, pkg.synthetic
+    n, base = 16384, 4096
+    tile = syn.smooth_cost_map(base, base, seed=20261018, obstacle_fraction=0.03)   # periodic fBm
+    cost = np.tile(tile, (n // base, n // base))
+    g0 = syn.free_interior_cell_near(tile <= 0, base // 2, base // 2)
+    goal = (g0[0] + (n // base // 2) * base, g0[1] + (n // base // 2) * base)
+    whole = api.DeviceLayer(n, n, device=0)
+    whole.set_cost_map(cost)
+    assert whole.solve_total_cost([goal])["converged"]
+    T1 = whole.download_total_cost()
+    whole.close()
+    layers, cuts = _strip_layers(pkg, cost, ng, list(range(ng)))
+    st = api.dd_solve([d for d, _ in layers], cuts, goal, 32)
+    assert st["converged"]
+    Tk = _gather_strips(layers)
+    assert np.array_equal(np.isinf(Tk), np.isinf(T1))
+    assert rel_err(Tk, T1) <= 1e-12
+
+
+def test_batch_solve_c_abi(pkg):
+    """dymu_batch_solve over two contexts (two GPUs if present, else both on GPU 0): every query's
+    plane and path equal the single-context result."""
+    import torch
+    api, syn = pkg.cuda_api, pkg.synthetic
+    n = 512
+    cost = syn.smooth_cost_map(n, n, seed=4)
+    ob = cost <= 0
+    rng = np.random.default_rng(3)
+    goals = [syn.free_interior_cell_near(ob, int(rng.uniform(0.1, 0.9) * n), int(rng.uniform(0.1, 0.9) * n))
+             for _ in range(11)]
+    starts = [syn.free_interior_cell_near(ob, int(rng.uniform(0.1, 0.9) * n), int(rng.uniform(0.1, 0.9) * n))
+              for _ in range(11)]
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    layers = []
+    for d in devs:
+        L = api.DeviceLayer(n, n, device=d)
+        L.set_cost_map(cost)
+        L.reserve_slots(4)
+        layers.append(L)
+    paths, ms = api.batch_solve(layers, goals, [[float(a), float(b)] for a, b in starts], cap=4096)
+    assert len(paths) == 11 and (ms > 0).all()
+    one = api.DeviceLayer(n, n, device=0)
+    one.set_cost_map(cost)
+    for q in (0, 5, 10):
+        one.solve_total_cost([goals[q]])
+        w, status = one.extract_global_path(float(starts[q][0]), float(starts[q][1]), 0.4, goals[q][0], goals[q][1])
+        got, gstatus = paths[q]
+        assert gstatus == status and got.shape[0] == len(w)
+        assert np.max(np.abs(got[:, :2] - w[:, :2])) <= 1e-9
