@@ -165,6 +165,17 @@ int dymu_solve_start(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t m
                      dymu_solve_stats* stats);
 int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, double seed_key,
                        uint32_t max_phases, dymu_solve_stats* stats);
+/* computeEntireTotalCostMap (G.cpp:443-468) again after cost, hazard_density or trafficability
+ * changed a little -- the local layer's feedback (L.cpp:264-274, 388-394) -- without starting
+ * over: cells whose cost term C (G.cpp:527-528) went up are found, everything that may have been
+ * computed from them (reachable along strictly increasing total cost) goes back to +inf, and only
+ * that region plus the tiles of cells whose C went down are propagated again.  Same fixed point
+ * as dymu_solve_total_cost.  Needs the resident map of slot 0 to be the converged solve of the
+ * same goal; otherwise, or when the invalidated cone does not fit its buffer (a quarter of the
+ * plane), it IS dymu_solve_total_cost.  cells_invalidated (optional): cells reset, UINT64_MAX
+ * when a full solve ran. */
+int dymu_solve_incremental(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, dymu_solve_stats* stats,
+                           uint64_t* cells_invalidated);
 /* setCostMap (G.cpp:109-126) without waiting for the copy: the rows around `first_row` (the
  * goal's row; >= ny = middle) are sent first on the copy stream, and the call returns at once.  The
  * next dymu_solve_total_cost with a single goal inside those first rows starts on them while the

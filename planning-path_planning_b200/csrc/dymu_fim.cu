@@ -836,7 +836,7 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
         else if (L.seed_kind != 3 && L.seed_kind != 1)
             DYMU_FAIL(ctx, DYMU_ERR_ARG, "a resumed solve takes tile-row seeds only");
     }
-    else
+    else if (!L.preseeded)
     {
         dymu_fim_work* w0 = L.work;
         if (w0->unclean)
@@ -1104,6 +1104,9 @@ static int solve_total_cost_impl(dymu_ctx* ctx, uint32_t n_goals, const uint32_t
         if (stats) stats[0] = local;
     }
     ctx->solved = (rc == DYMU_OK) && local.converged;
+    ctx->last_n_goals = n_goals;
+    ctx->last_goal_i = goal_i[0];
+    ctx->last_goal_j = goal_j[0];
     return rc;
 }
 

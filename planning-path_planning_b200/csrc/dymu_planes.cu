@@ -453,6 +453,7 @@ int dymu_destroy(dymu_ctx* ctx)
     DYMU_GUARD(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     dymu_internal_local_free(ctx);
+    dymu_internal_incremental_free(ctx);
     dymu_internal_fim_free(&ctx->work);
     void* ptrs[] = {ctx->elev, ctx->slope, ctx->raw, ctx->cost, ctx->haz, ctx->traff, ctx->ceff,
                     ctx->T, ctx->terrain, ctx->obst, ctx->locmode, ctx->d_lut, ctx->d_slopes,

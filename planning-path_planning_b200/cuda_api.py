@@ -73,6 +73,8 @@ _SIG = {
     "dymu_batch_solve": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, _u32p, _u32p, _dp, C.c_double,
                                    _dp, C.c_uint32, _u32p, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "dymu_local_reshape": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int64, C.c_int64]),
+    "dymu_solve_incremental": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(SolveStats),
+                                         C.POINTER(C.c_uint64)]),
     "dymu_set_cost_map_begin": (C.c_int, [C.c_void_p, _dp, C.c_size_t, C.c_uint32]),
     "dymu_set_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_size_t]),
     "dymu_compute_cost_map": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp,
@@ -291,6 +293,13 @@ class DeviceLayer:
         self._chk(self._l.dymu_solve_total_cost(self._h, g.shape[0], gi.ctypes.data_as(_u32p),
                                                 gj.ctypes.data_as(_u32p), C.byref(st)))
         return st.as_dict()
+
+    def solve_incremental(self, goal):
+        """Re-solve after small changes of cost / hazard_density / trafficability.  Returns
+        (stats, cells invalidated or None when a full solve ran)."""
+        st, inv = SolveStats(), C.c_uint64()
+        self._chk(self._l.dymu_solve_incremental(self._h, int(goal[0]), int(goal[1]), C.byref(st), C.byref(inv)))
+        return st.as_dict(), (None if inv.value == 2 ** 64 - 1 else int(inv.value))
 
     def solve_resume(self, ranges):
         """ranges: iterable of (j0, j1) row ranges whose tiles are re-activated."""

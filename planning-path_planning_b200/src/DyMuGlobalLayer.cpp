@@ -368,7 +368,7 @@ bool DyMuPathPlanner::computeTotalCostMap(base::Waypoint wPos)
         }
     uint32_t gi = goal_i, gj = goal_j;
     dymu_solve_stats st;
-    if (!deviceOk(dymu_solve_total_cost(dev, 1, &gi, &gj, &st), "computeTotalCostMap")) return false;
+    if (!deviceOk(dymu_solve_incremental(dev, gi, gj, &st, NULL), "computeTotalCostMap")) return false;
     double t_stop = kInf;
     if (!deviceOk(dymu_stop_threshold(dev, 0, si, sj, &t_stop), "computeTotalCostMap")) return false;
     closed_threshold = t_stop;
@@ -448,11 +448,15 @@ bool DyMuPathPlanner::computeEntireTotalCostMap()
     // "global_goal->isObstacle" (G.cpp:447) is left to the solve itself, which starts on the rows
     // that have arrived: a goal on an obstacle cell is not seeded and reported in the statistics.
     // (In that one case the previous total-cost map is already reset when false is returned.)
-    streamed_cost = false;
     uint32_t gi = goal_i, gj = goal_j;
     dymu_solve_stats st;
-    if (!deviceOk(dymu_solve_total_cost(dev, 1, &gi, &gj, &st), "computeEntireTotalCostMap"))
-        return false;
+    // A resident map of the same goal is re-solved incrementally: only what the changes of cost,
+    // hazard_density and trafficability since then can have touched (the local layer's feedback,
+    // L.cpp:264-274 and 388-394) is propagated again; anything else is a full solve.
+    int rc = streamed_cost ? dymu_solve_total_cost(dev, 1, &gi, &gj, &st)
+                           : dymu_solve_incremental(dev, gi, gj, &st, NULL);
+    streamed_cost = false;
+    if (!deviceOk(rc, "computeEntireTotalCostMap")) return false;
     if (st.goal_obstacle)
     {
         LOG_WARN_S << "The goal is not valid";

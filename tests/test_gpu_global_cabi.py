@@ -207,3 +207,48 @@ def test_two_contexts_on_two_devices_from_one_thread(pkg):
     fin = np.isfinite(out[0]) & (out[0] > 0)
     for T in out[1:]:
         assert np.max(np.abs(T[fin] - out[0][fin]) / out[0][fin]) <= 1e-13
+
+
+def test_incremental_resolve_equals_full_solve(pkg):
+    """dymu_solve_incremental after raising and lowering trafficability / hazard_density on patches
+    of global nodes (what a local repair feeds back, L.cpp:264-274, 388-394): same plane as a solve
+    from scratch, with only a part of the map invalidated."""
+    n = 768
+    syn, api = pkg.synthetic, pkg.cuda_api
+    cost = syn.smooth_cost_map(n, n, seed=12)
+    goal = syn.free_interior_cell_near(cost <= 0, 600, 560)
+    dev, ref = api.DeviceLayer(n, n), api.DeviceLayer(n, n)
+    dev.set_cost_map(cost)
+    ref.set_cost_map(cost)
+    st, inv = dev.solve_incremental(goal)
+    assert st["converged"] and inv is None                      # nothing resident yet: full solve
+    st, inv = dev.solve_incremental(goal)
+    assert st["converged"] and inv == 0 and st["tile_activations"] == 0   # nothing changed
+    rng = np.random.default_rng(2)
+    for step in range(3):
+        for d in (dev, ref):
+            r = np.random.default_rng(100 + step)
+            for _ in range(3):
+                i0, j0 = int(r.integers(40, 300)), int(r.integers(40, 300))
+                w, h = int(r.integers(3, 30)), int(r.integers(3, 30))
+                d.write_rect("trafficability", i0, j0, np.full((h, w), r.uniform(0.2, 0.9)))
+                i0, j0 = int(r.integers(40, 700)), int(r.integers(40, 700))
+                d.write_rect("hazard_density", i0, j0, np.full((4, 4), r.uniform(0.1, 0.6)))
+            if step == 2:   # costs going down again
+                d.write_rect("trafficability", 50, 50, np.ones((200, 200)))
+        st, inv = dev.solve_incremental(goal)
+        assert st["converged"] and inv is not None and 0 < inv < 0.25 * n * n, (step, inv)
+        full = ref.solve_total_cost([goal])
+        assert st["cell_updates"] < full["cell_updates"]
+        T, Tf = dev.download_total_cost(), ref.download_total_cost()
+        assert np.array_equal(np.isinf(T), np.isinf(Tf))
+        fin = np.isfinite(Tf) & (Tf > 0)
+        assert np.max(np.abs(T[fin] - Tf[fin]) / Tf[fin]) <= 1e-12, step
+    # another goal: not reusable, full solve
+    goal2 = syn.free_interior_cell_near(cost <= 0, 100, 100)
+    st, inv = dev.solve_incremental(goal2)
+    assert inv is None and st["converged"]
+    ref.solve_total_cost([goal2])
+    T, Tf = dev.download_total_cost(), ref.download_total_cost()
+    fin = np.isfinite(Tf) & (Tf > 0)
+    assert np.array_equal(np.isinf(T), np.isinf(Tf)) and np.max(np.abs(T[fin] - Tf[fin]) / Tf[fin]) <= 1e-13

@@ -301,3 +301,32 @@ def test_local_window_grows_and_keeps_obstacles(pkg, ref_lib, approach, monkeypa
     assert np.array_equal(aback > 0, bback > 0) and np.max(np.abs(aback - bback)) <= 1e-12
     assert np.array_equal(ha, hb), "hasLocalMap"
     assert np.max(np.abs(hza - hzb)) <= 1e-12 and np.max(np.abs(tra - trb)) <= 1e-9
+
+
+def test_two_repairs_with_incremental_resolve(pkg, ref_lib):
+    """repair -> trafficability / hazard feedback -> total-cost map
+    again -> new path -> second repair.  The reference solves from scratch each time; the drop-in
+    re-propagates only the dependency cone of the changed nodes (dymu_solve_incremental)."""
+    n, syn = 400, pkg.synthetic
+    res = []
+    for p in _pair(pkg, ref_lib, 1, n, n):
+        g = sc.global_scenario(p, syn, n, n, seed=9, entire=True)
+        r1 = _repair_at(p, syn, g["path"], 0, seed=31)
+        assert p.computeEntireTotalCostMap()                   # feedback -> re-solve
+        T1 = p.getTotalCostMatrix()
+        path = p.getPath(*g["path"][0, :2])
+        k1 = int(np.argmax(np.hypot(path[:, 0] - path[0, 0], path[:, 1] - path[0, 1]) > 25.0))
+        r2 = _repair_at(p, syn, path, k1, seed=32)
+        assert p.computeTotalCostMap(*path[k1, :2])
+        res.append((r1, T1, path, r2, p.getTotalCostMatrix(), p.node_field(5), p.getTrafficabilityMatrix()))
+    a, b = res
+    assert rel_err(b[6], a[6]) <= 1e-9 and (a[6] < 1.0).any(), "trafficability feedback"
+    assert np.array_equal(a[1] < 0, b[1] < 0) and rel_err(b[1], a[1]) <= TOL_PLANE
+    assert a[2].shape == b[2].shape and np.max(np.abs(a[2][:, :2] - b[2][:, :2])) <= TOL_WP
+    closed = a[5] > 0                                          # early stop: parity on the CLOSED set
+    assert np.array_equal(closed, b[5] > 0), "CLOSED set after the second re-solve"
+    assert rel_err(np.where(closed, b[4], 0), np.where(closed, a[4], 0)) <= TOL_PLANE
+    for k in (0, 3):
+        assert a[k]["repaired"] == b[k]["repaired"]
+        assert a[k]["traj"].shape == b[k]["traj"].shape
+        assert np.max(np.abs(a[k]["traj"][:, :2] - b[k]["traj"][:, :2])) <= TOL_WP
