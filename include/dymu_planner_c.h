@@ -132,6 +132,14 @@ int dymu_planner_recompute_cost_map(dymu_planner* p);
 
 /* seconds spent inside the last call of the given kind (wrapper-side
  * steady_clock around the forwarded method; conversions excluded) */
+/* Node-level steps of the reference class (H.hpp:520-536), on node (i, j) / waypoint (x, y):
+ * gradientNode G.cpp:718-772; computeNextGlobalWaypoint G.cpp:666-714 (out = next x, next y,
+ * heading, interpolated z of the input waypoint); propagateGlobalNode G.cpp:500-546 (returns the
+ * node's total cost after the update).  Return 0 when the node does not exist. */
+int dymu_planner_gradient_node(dymu_planner* p, unsigned i, unsigned j, double* dnx, double* dny);
+int dymu_planner_next_global_waypoint(dymu_planner* p, double x, double y, double tau, double out[4]);
+int dymu_planner_propagate_global_node(dymu_planner* p, unsigned i, unsigned j, double* total_cost);
+
 /* Copy-free variants (extensions of the B200 drop-in; the reference build implements them on top
  * of the by-value methods so that the same call sequence runs on both):
  *   set_cost_map_flat          setCostMap(const double*, ld) -- with a goal in place the upload is

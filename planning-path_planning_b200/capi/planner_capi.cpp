@@ -406,6 +406,39 @@ int dymu_planner_get_node_field(dymu_planner* p, int field, double* out)
 #endif
 }
 
+int dymu_planner_gradient_node(dymu_planner* p, unsigned i, unsigned j, double* dnx, double* dny)
+{
+    if (!p || !dnx || !dny) return -1;
+    PathPlanning_lib::globalNode* g = p->impl->getGlobalNode(i, j);
+    if (!g) return 0;
+    p->impl->gradientNode(g, *dnx, *dny);
+    return 1;
+}
+
+int dymu_planner_next_global_waypoint(dymu_planner* p, double x, double y, double tau, double out[4])
+{
+    if (!p || !out) return -1;
+    base::Waypoint w;
+    w.position[0] = x;
+    w.position[1] = y;
+    base::Waypoint nx = p->impl->computeNextGlobalWaypoint(w, tau);
+    out[0] = nx.position[0];
+    out[1] = nx.position[1];
+    out[2] = nx.heading;
+    out[3] = w.position[2];
+    return 1;
+}
+
+int dymu_planner_propagate_global_node(dymu_planner* p, unsigned i, unsigned j, double* total_cost)
+{
+    if (!p || !total_cost) return -1;
+    PathPlanning_lib::globalNode* g = p->impl->getGlobalNode(i, j);
+    if (!g) return 0;
+    p->impl->propagateGlobalNode(g);
+    *total_cost = g->total_cost;
+    return 1;
+}
+
 int dymu_planner_set_cost_map_flat(dymu_planner* p, const double* cost, unsigned ld)
 {
     if (!p || !cost || ld < p->nx) return -1;

@@ -53,6 +53,9 @@ _SIGNATURES = {
     "dymu_planner_update_cost": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "dymu_planner_compute_cost_ratio": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "dymu_planner_recompute_cost_map": (C.c_int, [C.c_void_p]),
+    "dymu_planner_gradient_node": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, _dp, _dp]),
+    "dymu_planner_next_global_waypoint": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp]),
+    "dymu_planner_propagate_global_node": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, _dp]),
     "dymu_planner_set_cost_map_flat": (C.c_int, [C.c_void_p, _dp, C.c_uint]),
     "dymu_planner_set_total_cost_target": (C.c_int, [C.c_void_p, _dp, C.c_uint]),
     "dymu_planner_get_total_cost_matrix_flat": (C.c_int, [C.c_void_p, _dp, C.c_uint]),
@@ -131,6 +134,25 @@ class Planner:
                 or a.strides[1] != 8 or a.strides[0] % 8 or a.strides[0] < 8 * nx):
             raise ValueError("expected a float64 array of shape (%d, %d) with contiguous rows" % (ny, nx))
         return a, a.strides[0] // 8
+
+    def gradientNode(self, i, j):
+        """(dnx, dny) of global node (i, j), or None when it does not exist."""
+        a, b = C.c_double(), C.c_double()
+        if self._l.dymu_planner_gradient_node(self._h, int(i), int(j), C.byref(a), C.byref(b)) != 1:
+            return None
+        return a.value, b.value
+
+    def computeNextGlobalWaypoint(self, x, y, tau):
+        """(next x, next y, heading, z of the input waypoint)."""
+        out = np.zeros(4)
+        self._l.dymu_planner_next_global_waypoint(self._h, x, y, tau, _ptr(out))
+        return out
+
+    def propagateGlobalNode(self, i, j):
+        t = C.c_double()
+        if self._l.dymu_planner_propagate_global_node(self._h, int(i), int(j), C.byref(t)) != 1:
+            return None
+        return t.value
 
     def setCostMapFlat(self, cost_map):
         """setCostMap(const double*, ld) of the drop-in: no nesting, and with a goal in place the

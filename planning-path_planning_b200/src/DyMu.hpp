@@ -209,6 +209,11 @@ class DyMuPathPlanner
                         std::vector<std::vector<double>> elevation,
                         std::vector<std::vector<double>> terrainMap);
 
+    // Node-level steps (reference: H.hpp:497-575), forwards onto value views: DyMuNodeLevel.cpp
+    void calculateSlope(globalNode* nodeTarget);
+    void calculateNominalCost(globalNode* nodeTarget, int range, int numLocs);
+    void smoothCost(globalNode* nodeTarget);
+
     // Returns a view of global node (i,j), NULL if out of range
     globalNode* getGlobalNode(uint i, uint j);
 
@@ -223,12 +228,18 @@ class DyMuPathPlanner
     void resetTotalCostMap();
     void resetGlobalNarrowBand();
 
+    void propagateGlobalNode(globalNode* nodeTarget);
+    globalNode* minCostGlobalNode();
+
     globalNode* getNearestGlobalNode(base::Pose2D pos);
     globalNode* getNearestGlobalNode(base::Waypoint wPos);
 
     std::vector<base::Waypoint> getPath(base::Waypoint wPos);
 
     bool computeGlobalPath(base::Waypoint wPos);
+
+    base::Waypoint computeNextGlobalWaypoint(base::Waypoint& wPos, double tau);
+    void gradientNode(globalNode* nodeTarget, double& dnx, double& dny);
 
     double interpolate(double a, double b, double g00, double g01, double g10, double g11);
 
@@ -242,6 +253,7 @@ class DyMuPathPlanner
     double getTotalCost(base::Waypoint wInt);
 
     // LOCAL PATH REPAIRING
+    void createLocalMap(globalNode* gNode);
     localNode* getLocalNode(base::Pose2D pos);
     localNode* getLocalNode(base::Waypoint wPos);
 
@@ -254,14 +266,25 @@ class DyMuPathPlanner
                               base::Time& localTime);
 
     void expandRisk();
+    localNode* maxRiskNode();
+    void propagateRisk(localNode* nodeTarget);
+    void setHorizonCost(localNode* horizonNode);
 
     double getTotalCost(localNode* lNode);
 
     localNode* computeLocalPropagation(base::Waypoint wInit, base::Waypoint wOvertake);
+    void propagateLocalNode(localNode* nodeTarget);
+    localNode* minCostLocalNode(double Tovertake, double minC);
+    localNode* minCostLocalNode(localNode* reachNode);
 
     std::vector<base::Waypoint> getLocalPath(localNode* lSetNode, base::Waypoint wInit, double tau);
 
+    bool computeLocalWaypointGDM(base::Waypoint& wPos, double tau);
+    base::Waypoint computeLocalWaypointDijkstra(localNode* lNode);
+    void gradientNode(localNode* nodeTarget, double& dnx, double& dny);
+
     bool evaluatePath(uint starting_index);
+    bool isBlockingObstacle(localNode* obNode, uint& maxIndex, uint& minIndex);
 
     int repairPath(base::Waypoint wInit, uint index);
 

@@ -148,3 +148,41 @@ def test_total_cost_queries_and_node_views(pkg, ref_lib):
     fin = np.isfinite(a)
     assert np.array_equal(fin, np.isfinite(b))
     assert np.max(np.abs(a[fin] - b[fin]) / np.maximum(1e-300, np.abs(a[fin]))) <= 1e-9
+
+
+def test_node_level_forwards(pkg, ref_lib):
+    """gradientNode, computeNextGlobalWaypoint and propagateGlobalNode (H.hpp:520-536) called from
+    outside, on the reference's pointer graph and on the drop-in's node views."""
+    nx, ny = 96, 80
+    elev, terr = pkg.synthetic.mars_dem(ny, nx, seed=7)      # (setCostMap alone leaves the reference's
+    lut, slopes, locs = pkg.synthetic.default_lut()          #  elevation uninitialised, H.hpp:95)
+    out = []
+    for p in _both(pkg, ref_lib, nx=nx, ny=ny):
+        assert p.computeCostMap(lut, slopes, locs, elev, terr)
+        ob = sc.obstacle_plane(p)
+        gi, gj = pkg.synthetic.free_interior_cell_near(ob, 70, 60)
+        assert p.setGoal(gi, gj) and p.computeEntireTotalCostMap()
+        T = p.getTotalCostMatrix()
+        rec = []
+        # (the reference dereferences a missing neighbour when the other one is unreached,
+        # G.cpp:729-731: border nodes next to the obstacle rim cannot be asked there)
+        for (i, j) in ((40, 30), (gi, gj), (gi + 1, gj), (17, 63), (3, 3), (nx - 4, ny - 4)):
+            rec.append(p.gradientNode(i, j))
+        # next to an unreached / obstacle cell: one-sided differences
+        jj, ii = np.nonzero(T < 0)
+        for k in range(0, len(ii), max(1, len(ii) // 6)):
+            if 1 < ii[k] < nx - 3 and 1 < jj[k] < ny - 2:
+                rec.append(p.gradientNode(int(ii[k]) + 1, int(jj[k])))
+        steps = [p.computeNextGlobalWaypoint(x, y, 0.4) for x, y in ((20.3, 15.8), (60.0, 40.0), (gi - 3.2, gj + 2.1))]
+        # a converged node cannot be improved; a node whose value is raised by hand comes back down
+        same = p.propagateGlobalNode(40, 30)
+        out.append((rec, steps, same, T[30, 40]))
+        assert p.gradientNode(nx + 5, 3) is None
+    (ra, sa, ta, Ta), (rb, sb, tb, Tb) = out
+    assert len(ra) == len(rb)
+    for a, b in zip(ra, rb):
+        assert np.allclose(a, b, rtol=0, atol=1e-9, equal_nan=True), (a, b)
+    for a, b in zip(sa, sb):
+        assert np.max(np.abs(a[:2] - b[:2])) <= 1e-9 and abs(a[3] - b[3]) <= 1e-9
+        assert abs(np.angle(np.exp(1j * (a[2] - b[2])))) <= 1e-9
+    assert ta == pytest.approx(Ta, rel=1e-12) and tb == pytest.approx(Tb, rel=1e-12)
