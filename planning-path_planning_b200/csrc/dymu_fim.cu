@@ -212,7 +212,11 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ts = reinterpret_cast<double*>(smem_raw);            // (TILE+2) x P, 1-cell halo
     double* Cs = Ts + (TILE + 2) * P;                            // TILE x P
-    __shared__ uint32_t dmask[3];  // dirty 8x4 blocks: being swept / for the next sweep / being reset
+    // dirty 8x8 blocks for the next sweep: every warp posts what its block visit woke up into its own
+    // word (plain store, two sets alternating by sweep parity); after the barrier each warp ORs the
+    // sixteen words with one warp reduction -- no shared-memory atomics in the sweep
+    __shared__ uint32_t s_post[2][K::WARPS];
+    __shared__ uint32_t s_m0;      // dirty set an activation starts with
     __shared__ uint32_t edge_mask;  // tile edges with a changed cell: 1 top, 2 bottom, 4 left, 8 right
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_emin[5];  // min changed value per edge [0..3], overall [4]
@@ -327,7 +331,11 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                         first_fetch = false;
                     }
                     else
+                    {
+                        // no shared cursor to ask when every entry was pre-assigned
+                        if (n_active <= gridDim.x) break;
                         idx = gridDim.x + atomicAdd(&p.ctrl[3 + cur], 1u);
+                    }
                     if (idx >= n_active) break;
                     const uint32_t cand = ld_volatile_u32(&list_cur[idx]);
                     const unsigned long long k = ld_volatile_u64(&key_cur[cand]);
@@ -419,9 +427,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 if (why & kHaloBottom) m0 |= 0xF000u;                        // by == BY-1
                 if (why & kHaloLeft) m0 |= 0x1111u;                          // bx == 0
                 if (why & kHaloRight) m0 |= 0x8888u;                         // bx == BX-1
-                dmask[0] = m0;
-                dmask[1] = 0;
-                dmask[2] = 0;
+                s_m0 = m0;
                 flag_cur[tile_id] = 0;  // consumed; writers use flag_nxt / key_nxt this phase
                 key_cur[tile_id] = kNoKey;
             }
@@ -439,7 +445,8 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             // therefore one visit per warp, whatever the number of dirty blocks.
             int it = 0;
             uint32_t visits = 0;
-            uint32_t m = dmask[0];
+            uint32_t m = s_m0;
+            uint32_t edges_acc = 0;  // warp-uniform: tile edges this warp's block changed (bits 0..3)
             const int cap = min(p.inner_cap, budget);
             double cA[K::NB], cB[K::NB], qA[K::NB], qB[K::NB];
 #pragma unroll
@@ -450,10 +457,9 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 qA[h] = 2 * (cA[h] * cA[h]);
                 qB[h] = 2 * (cB[h] * cB[h]);
             }
-            // one sweep: relax the dirty blocks listed in m, collect the next dirty set in *nxt,
-            // clear *old for the sweep after that; returns the next dirty set
-            auto sweep = [&](uint32_t* nxt, uint32_t* old) -> uint32_t {
-                if (tid == 0) *old = 0;
+            // one sweep: relax the dirty blocks listed in m; returns the next dirty set
+            auto sweep = [&](uint32_t* post) -> uint32_t {
+                uint32_t contrib = 0;
 #pragma unroll
                 for (int h = 0; h < K::NB; ++h)
                 {
@@ -477,29 +483,23 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     if (chB) b[0] = nB;
                     // one warp reduction tells which blocks (bits 0..15) and which tile edges
                     // (bits 16..19) saw a change
-                    const uint32_t all = __reduce_or_sync(0xffffffffu, (chA ? wake.x : 0u) | (chB ? wake.y : 0u));
+                    contrib |= __reduce_or_sync(0xffffffffu, (chA ? wake.x : 0u) | (chB ? wake.y : 0u));
                     visits += 2;
-                    if (all != 0 && lane == 0)
-                    {
-                        smem_or(nxt, all & 0xffffu);
-                        if (all >> 16) smem_or(&edge_mask, all >> 16);
-                    }
                 }
+                edges_acc |= contrib >> 16;
+                if (lane == 0) post[warp] = contrib & 0xffffu;
                 __syncthreads();
                 ++it;
-                return *nxt;
+                return __reduce_or_sync(0xffffffffu, post[lane & (K::WARPS - 1)]);
             };
-            // the three mask words rotate through the roles current / next / being cleared;
-            // unrolled by three so that their addresses are constants
             for (;;)
             {
                 if (m == 0 || it >= cap) break;
-                m = sweep(&dmask[1], &dmask[2]);
+                m = sweep(s_post[0]);
                 if (m == 0 || it >= cap) break;
-                m = sweep(&dmask[2], &dmask[0]);
-                if (m == 0 || it >= cap) break;
-                m = sweep(&dmask[0], &dmask[1]);
+                m = sweep(s_post[1]);
             }
+            if (edges_acc && lane == 0) smem_or(&edge_mask, edges_acc);
             n_visits += visits;
             const int more = (m != 0);
             if (more && tid == 0) p.dsave[tile_id] = m;
