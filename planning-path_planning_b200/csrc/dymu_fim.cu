@@ -60,9 +60,11 @@ template <int TILE> struct Cfg
     static constexpr int NB = 16 / WARPS;         // blocks per warp: block b = warp + h * WARPS
     static constexpr int BX = TILE / 8;       // 4 x 4 blocks of 8 x 8 cells, block w <-> warp w
     static constexpr int BY = TILE / 8;
-    // row pitch of the shared arrays in doubles; PITCH % 16 == 8 makes consecutive 8-double
-    // rows of a block fall into disjoint bank groups (conflict-free 64-bit access)
-    static constexpr int PITCH = TILE + 8;
+    // row pitch of the shared arrays in doubles.  A half-warp (what one 64-bit shared-memory
+    // transaction serves) touches four consecutive rows of a block, every other column of each
+    // (red-black ownership, see k_fim): with 36 doubles = 72 words per row the rows start 8
+    // banks apart and the four groups of alternate columns fall into disjoint banks
+    static constexpr int PITCH = TILE + 4;
     static constexpr int CPT = TILE * TILE / THREADS;  // cells per thread in load/store = 2
     static constexpr int MIN_CTAS = 32 / WARPS;   // 1024 threads per SM either way
     static constexpr size_t SMEM = sizeof(double) * ((TILE + 2) * PITCH + TILE * PITCH);
@@ -224,34 +226,43 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_per_prob = p.ntx * p.nty;
     // ---- per-thread constants of the sweep.  Warp w owns the 8x8 block(s) b = w + h * WARPS
-    // (bx = b & 3, by = b >> 2); lane (lx, ly) owns the cells (lx, ly) and (lx, ly + 4) of it,
-    // whose two update chains are independent and interleave in the in-order issue stream.
-    // wakeA / wakeB: what a change of the lane's upper / lower cell has to wake up -- the own
-    // block, the neighbour block across a block edge (bits 0..15) and the tile edge the cell
-    // sits on (bits 16..19: top, bottom, left, right).
+    // (bx = b & 3, by = b >> 2); lane (lx, ly) owns the two cells (lx, 2 ly) and (lx, 2 ly + 1) of
+    // it, one of each colour of the checkerboard (x + y even = red).  A block visit relaxes the
+    // red cells of the block first and the black ones after a __syncwarp, so the black cells see
+    // this very visit's red values: information moves two cells per sweep instead of one
+    // (red-black Gauss-Seidel inside the block, Jacobi between the blocks), which halves the
+    // sweeps a wave needs to cross a tile at the same instruction count per sweep.
+    // wake.x / wake.y: what a change of the lane's first (red) / second (black) cell has to wake
+    // up -- the own block, the neighbour block across a block edge (bits 0..15) and the tile
+    // edge the cell sits on (bits 16..19: top, bottom, left, right).
     // The masks live in shared memory: kept in registers the compiler re-derives them from the
     // thread index in every sweep (64-register cap), which costs more issue slots than one load.
     constexpr int c_off = (TILE + 1) * P - 1;  // from a cell of Ts to the same cell of Cs
     __shared__ uint2 s_wake[K::NB][K::THREADS];
-    double* cellA[K::NB];
+    double* cell1[K::NB];   // the lane's red cell
+    int to_second;          // offset (doubles) from the red to the black cell: +P or -P
     uint32_t my_bit[K::NB];
     {
         const int lx = lane & 7, ly = lane >> 3;
+        const bool upper_is_red = (lx & 1) == 0;  // rows 2 ly (upper) and 2 ly + 1 (lower)
+        to_second = upper_is_red ? P : -P;
+        asm volatile("" : "+r"(to_second));
 #pragma unroll
         for (int h = 0; h < K::NB; ++h)
         {
             const int b = warp + h * K::WARPS;
             const int bx = b & 3, by = b >> 2;
             // opaque offset: otherwise it is re-derived from the thread index in every sweep
-            int off = (by * 8 + ly + 1) * P + bx * 8 + lx + 1;
+            int off = (by * 8 + 2 * ly + (upper_is_red ? 0 : 1) + 1) * P + bx * 8 + lx + 1;
             asm volatile("" : "+r"(off));
-            cellA[h] = Ts + off;
+            cell1[h] = Ts + off;
             my_bit[h] = 1u << b;
             const uint32_t bitL = bx > 0 ? my_bit[h] >> 1 : 0x40000u, bitR = bx < K::BX - 1 ? my_bit[h] << 1 : 0x80000u;
             const uint32_t bitU = by > 0 ? my_bit[h] >> 4 : 0x10000u, bitD = by < K::BY - 1 ? my_bit[h] << 4 : 0x20000u;
             const uint32_t side = (lx == 0 ? bitL : 0u) | (lx == 7 ? bitR : 0u);
-            s_wake[h][tid] = make_uint2(my_bit[h] | side | (ly == 0 ? bitU : 0u),
-                                        my_bit[h] | side | (ly == 3 ? bitD : 0u));
+            const uint32_t w_upper = my_bit[h] | side | (ly == 0 ? bitU : 0u);
+            const uint32_t w_lower = my_bit[h] | side | (ly == 3 ? bitD : 0u);
+            s_wake[h][tid] = upper_is_red ? make_uint2(w_upper, w_lower) : make_uint2(w_lower, w_upper);
         }
     }
     auto sel3 = [](uint32_t* a, uint32_t* b, uint32_t* c, int k) { return k == 0 ? a : (k == 1 ? b : c); };
@@ -452,8 +463,8 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 #pragma unroll
             for (int h = 0; h < K::NB; ++h)
             {
-                cA[h] = cellA[h][c_off];
-                cB[h] = cellA[h][4 * P + c_off];
+                cA[h] = cell1[h][c_off];
+                cB[h] = cell1[h][to_second + c_off];
                 qA[h] = 2 * (cA[h] * cA[h]);
                 qB[h] = 2 * (cB[h] * cB[h]);
             }
@@ -464,22 +475,24 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 for (int h = 0; h < K::NB; ++h)
                 {
                     if (!(m & my_bit[h])) continue;
-                    double* a = cellA[h];
-                    double* b = a + 4 * P;
+                    double* a = cell1[h];
+                    double* b = a + to_second;
                     // requested with the cell values and pinned here: left to the compiler the
                     // load sinks below the update and its latency lands on the chain
                     uint2 wake = s_wake[h][tid];
                     asm volatile("" : "+r"(wake.x), "+r"(wake.y));
+                    // red cells of the block ...
                     double tA = a[0];
                     const double lA = a[-1], rA = a[1], uA = a[-P], dA = a[P];
                     asm volatile("" : "+d"(tA));
-                    double tB = b[0];
-                    const double lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
-                    asm volatile("" : "+d"(tB));  // keep the two "current value" loads up here too
                     double nA, nB;
                     const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], qA[h], nA);
-                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], qB[h], nB);
                     if (chA) a[0] = nA;
+                    __syncwarp();
+                    // ... then the black ones, on the red values just stored
+                    const double tB = b[0];
+                    const double lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
+                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], qB[h], nB);
                     if (chB) b[0] = nB;
                     // one warp reduction tells which blocks (bits 0..15) and which tile edges
                     // (bits 16..19) saw a change

@@ -127,8 +127,11 @@ def test_overlapped_total_cost_download(pkg):
     assert np.array_equal(got, want)
     assert status == 0 and len(wps) > 10
     # and the context keeps working afterwards
+    # (two solves agree to rounding, not bit for bit: blocks of a tile read each other's cells
+    # while they are being relaxed, and floating-point evaluation is not exactly monotone)
     dev.solve_total_cost([goal])
-    assert np.array_equal(dev.download_total_cost(xform=pkg.cuda_api.XFORM_INF_TO_MINUS1), want)
+    again = dev.download_total_cost(xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
+    assert np.array_equal(again < 0, want < 0) and rel_err(again, want) <= 1e-13
 
 
 @pytest.mark.parametrize("goal_xy,first_phases", [((150, 300), 3), ((40, 20), 1), ((200, 590), 50)])
