@@ -51,6 +51,9 @@ namespace
 template <int TILE> struct Cfg
 {
     static_assert(TILE == 32, "4 x 4 blocks of 8 x 8 cells");
+#ifndef DYMU_FIM_ROUNDS
+#define DYMU_FIM_ROUNDS 4  // red-black rounds per block visit (an unchanged block stops early)
+#endif
 #ifndef DYMU_FIM_WARPS
 #define DYMU_FIM_WARPS 16
 #endif
@@ -481,23 +484,34 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     // load sinks below the update and its latency lands on the chain
                     uint2 wake = s_wake[h][tid];
                     asm volatile("" : "+r"(wake.x), "+r"(wake.y));
-                    // red cells of the block ...
-                    double tA = a[0];
-                    const double lA = a[-1], rA = a[1], uA = a[-P], dA = a[P];
-                    asm volatile("" : "+d"(tA));
-                    double nA, nB;
-                    const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], qA[h], nA);
-                    if (chA) a[0] = nA;
-                    __syncwarp();
-                    // ... then the black ones, on the red values just stored
-                    const double tB = b[0];
-                    const double lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
-                    const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], qB[h], nB);
-                    if (chB) b[0] = nB;
+                    uint32_t woke = 0;
+#pragma unroll
+                    for (int round = 0; round < DYMU_FIM_ROUNDS; ++round)
+                    {
+                        // red cells of the block ...
+                        double tA = a[0];
+                        const double lA = a[-1], rA = a[1], uA = a[-P], dA = a[P];
+                        asm volatile("" : "+d"(tA));
+                        double nA, nB;
+                        const bool chA = relax<MODE>(tA, lA, rA, uA, dA, cA[h], qA[h], nA);
+                        if (chA) a[0] = nA;
+                        __syncwarp();
+                        // ... then the black ones, on the red values just stored
+                        const double tB = b[0];
+                        const double lB = b[-1], rB = b[1], uB = b[-P], dB = b[P];
+                        const bool chB = relax<MODE>(tB, lB, rB, uB, dB, cB[h], qB[h], nB);
+                        if (chB) b[0] = nB;
+                        woke |= (chA ? wake.x : 0u) | (chB ? wake.y : 0u);
+                        visits += 2;
+                        if (round + 1 < DYMU_FIM_ROUNDS)
+                        {
+                            // another round only pays while the block is still changing
+                            if (!__any_sync(0xffffffffu, chA || chB)) break;
+                        }
+                    }
                     // one warp reduction tells which blocks (bits 0..15) and which tile edges
                     // (bits 16..19) saw a change
-                    contrib |= __reduce_or_sync(0xffffffffu, (chA ? wake.x : 0u) | (chB ? wake.y : 0u));
-                    visits += 2;
+                    contrib |= __reduce_or_sync(0xffffffffu, woke);
                 }
                 edges_acc |= contrib >> 16;
                 if (lane == 0) post[warp] = contrib & 0xffffu;
