@@ -536,25 +536,45 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 #endif
 
             // ---- write back changed cells and wake the neighbours whose halo went stale
-#pragma unroll
-            for (int k = 0; k < K::CPT; ++k)
             {
-                int e = tid + k * K::THREADS;
-                int y = e / TILE, x = e % TILE;
-                double v = Ts[(y + 1) * P + x + 1];
-                if (v != told[k])
+                // smallest new value per tile edge = the priority the neighbour gets; [4]: smallest
+                // new value anywhere, the tile's own priority when it has to be continued
+                unsigned long long kmin[5] = {kNoKey, kNoKey, kNoKey, kNoKey, kNoKey};
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < K::CPT; ++k)
                 {
-                    n_written++;
-                    __stcg(&Tg[(size_t)y * p.pitch + x], v);
-                    if (MODE == 0)
+                    int e = tid + k * K::THREADS;
+                    int y = e / TILE, x = e % TILE;
+                    double v = Ts[(y + 1) * P + x + 1];
+                    if (v != told[k])
                     {
-                        // smallest new value per tile edge = the priority the neighbour gets
-                        const unsigned long long kb = key_of(v);
-                        if (y == 0) atomicMin(&s_emin[0], kb);
-                        if (y == TILE - 1) atomicMin(&s_emin[1], kb);
-                        if (x == 0) atomicMin(&s_emin[2], kb);
-                        if (x == TILE - 1) atomicMin(&s_emin[3], kb);
-                        if (more) atomicMin(&s_emin[4], kb);
+                        n_written++;
+                        __stcg(&Tg[(size_t)y * p.pitch + x], v);
+                        if (MODE == 0)
+                        {
+                            const unsigned long long kb = key_of(v);
+                            any = true;
+                            if (y == 0) kmin[0] = min(kmin[0], kb);
+                            if (y == TILE - 1) kmin[1] = min(kmin[1], kb);
+                            if (x == 0) kmin[2] = min(kmin[2], kb);
+                            if (x == TILE - 1) kmin[3] = min(kmin[3], kb);
+                            if (more) kmin[4] = min(kmin[4], kb);
+                        }
+                    }
+                }
+                if (MODE == 0 && __any_sync(0xffffffffu, any))
+                {
+                    // one shared-memory atomic per warp and edge instead of one per cell (64-bit
+                    // shared-memory minima are compare-and-swap loops)
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                    {
+                        const uint32_t hi = (uint32_t)(kmin[q] >> 32), lo = (uint32_t)kmin[q];
+                        const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+                        const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+                        const unsigned long long r = ((unsigned long long)mhi << 32) | mlo;
+                        if (lane == 0 && r != kNoKey) atomicMin(&s_emin[q], r);
                     }
                 }
             }
