@@ -105,7 +105,11 @@ __global__ void k_slope_nominal(const double* __restrict__ elev,
         double rawc = 0.0;
         bool ob = false;
         uint8_t lm = locmode[q];
-        if (terr == 0)
+        // a terrain class whose rows lie beyond the table (the reference would read past the end of
+        // cost_lutable) is impassable like class 0
+        const bool off_table = (unsigned long long)(terr + 1) * (unsigned)n_slopes * (unsigned)n_locs
+                               > (unsigned long long)n_lut;
+        if (terr == 0 || off_table)
         {
             rawc = Cmax;
             ob = true;
