@@ -553,12 +553,17 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                         __stcg(&Tg[(size_t)y * p.pitch + x], v);
                         if (MODE == 0)
                         {
+                            // A neighbouring tile only has to look again if this cell dropped below
+                            // the cell facing it across the edge: the update is upwind, a cell is
+                            // never improved through a neighbour that is not smaller, and the halo
+                            // value is an upper bound of what the facing cell holds by now.  This
+                            // drops the wake-ups a tile would send to the tiles it was fed from.
                             const unsigned long long kb = key_of(v);
                             any = true;
-                            if (y == 0) kmin[0] = min(kmin[0], kb);
-                            if (y == TILE - 1) kmin[1] = min(kmin[1], kb);
-                            if (x == 0) kmin[2] = min(kmin[2], kb);
-                            if (x == TILE - 1) kmin[3] = min(kmin[3], kb);
+                            if (y == 0 && v < Ts[x + 1]) kmin[0] = min(kmin[0], kb);
+                            if (y == TILE - 1 && v < Ts[(TILE + 1) * P + x + 1]) kmin[1] = min(kmin[1], kb);
+                            if (x == 0 && v < Ts[(y + 1) * P]) kmin[2] = min(kmin[2], kb);
+                            if (x == TILE - 1 && v < Ts[(y + 1) * P + TILE + 1]) kmin[3] = min(kmin[3], kb);
                             if (more) kmin[4] = min(kmin[4], kb);
                         }
                     }
@@ -586,7 +591,10 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             if (tid < 5)
             {
                 uint32_t target = 0xffffffffu, bit = 0;
-                const uint32_t em = edge_mask;
+                uint32_t em = edge_mask;
+                if (MODE == 0)  // only the edges across which a value can actually travel
+                    em = (s_emin[0] != kNoKey ? 1u : 0u) | (s_emin[1] != kNoKey ? 2u : 0u)
+                         | (s_emin[2] != kNoKey ? 4u : 0u) | (s_emin[3] != kNoKey ? 8u : 0u);
                 if (tid == 0 && (em & 1u) && ty > 0) { target = tile_id - p.ntx; bit = kHaloBottom; }
                 if (tid == 1 && (em & 2u) && ty + 1 < p.nty) { target = tile_id + p.ntx; bit = kHaloTop; }
                 if (tid == 2 && (em & 4u) && tx > 0) { target = tile_id - 1; bit = kHaloRight; }
