@@ -211,6 +211,25 @@ def run_reference(args):
               "cells, which flatters the reference (its narrow-band scan scales ~x16 per "
               "doubling: 3152 s measured for one 4096^2 solve in BASELINE.md)"
               % (cores, crop, crop, frac, n, n))
+    # same configuration, different container: the pinned C port of the reference's update with a
+    # binary heap instead of the reference's linear narrow-band scan, full map, one core
+    same_config = None
+    try:
+        q = oracle.Port(1.0, 1.5, 2.0, 1)
+        q.initGlobalLayer(1.0, 0.1, n, n)
+        q.computeCostMap(lut, slopes, locs, elev, terr)
+        g2 = pkg.synthetic.free_interior_cell_near(q.plane("isObstacle"), n // 2, n // 2)
+        q.setGoal(*g2)
+        t1 = time.perf_counter()
+        q.computeEntireTotalCostMap(heap=True)
+        q.getPath(float(n // 8), float(n // 8))
+        dt_full = time.perf_counter() - t1
+        q.close()
+        same_config = {"seconds_per_plan": dt_full, "plans_per_s_per_core": 1.0 / dt_full, "cores": 1,
+                       "kind": "port (oracle/dymu_oracle.c, heap-ordered; the unmodified reference needs "
+                               "3152 s for this solve, BASELINE.md)"}
+    except Exception as e:
+        same_config = {"error": str(e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -223,6 +242,7 @@ def run_reference(args):
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "same_config_full_map": same_config,
     }
     print(json.dumps(line))
     return 0
@@ -353,7 +373,10 @@ class Dist:
         store = self.dist.distributed_c10d._get_default_store()
         key = "bench_host_barrier_" + name
         store.add(key, 1)
+        t0 = time.perf_counter()
         while store.add(key, 0) < self.world:
+            if time.perf_counter() - t0 > 900.0:
+                raise RuntimeError("bench.py: rank %d waited 15 min at host barrier %s" % (self.rank, name))
             time.sleep(0.002)
 
     def max(self, values):

@@ -52,7 +52,7 @@ template <int TILE> struct Cfg
 {
     static_assert(TILE == 32, "4 x 4 blocks of 8 x 8 cells");
 #ifndef DYMU_FIM_ROUNDS
-#define DYMU_FIM_ROUNDS 4  // red-black rounds per block visit (an unchanged block stops early)
+#define DYMU_FIM_ROUNDS 6  // red-black rounds per block visit (an unchanged block stops early)
 #endif
 #ifndef DYMU_FIM_WARPS
 #define DYMU_FIM_WARPS 16

@@ -1,10 +1,11 @@
 #!/bin/bash
-out=gpurun_out/exp_fim14.log
+out=gpurun_out/exp_fim15.log
 : > $out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 >> $out
-for B in 3 4 5 6; do
-    echo "=== band=$B" >> $out
-    DYMU_FIM_BAND=$B timeout 120 python scripts/probe_solve.py --n 4096 --reps 3 --nopath 2>&1 | grep "rep 2" >> $out
+for R in 5 6 8; do
+  DYMU_FIM_ROUNDS=$R python planning-path_planning_b200/build.py --force > /dev/null 2>&1
+  echo "=== rounds=$R" >> $out
+  for k in 1 2; do timeout 120 python scripts/probe_solve.py --n 4096 --reps 4 --nopath 2>&1 | grep "rep 3" >> $out; done
 done
-echo "=== 16384" >> $out
-timeout 300 python scripts/probe_solve.py --n 16384 --reps 2 --nopath --kind smooth 2>&1 | grep "rep" >> $out
+python planning-path_planning_b200/build.py --force > /dev/null 2>&1
+echo "=== rounds=4 (default)" >> $out
+for k in 1 2; do timeout 120 python scripts/probe_solve.py --n 4096 --reps 4 --nopath 2>&1 | grep "rep 3" >> $out; done
