@@ -1433,6 +1433,7 @@ static int import_rows_impl(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t 
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_flag, 16, cudaMemcpyDeviceToHost, ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *changed = (int)(h[0] & 0xffffffffu);
+    if (*changed) ctx->solved = false;  // the plane moved away from the last solve's fixed point
     if (min_lowered)
     {
         long long bits = (long long)h[1];

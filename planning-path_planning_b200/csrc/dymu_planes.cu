@@ -532,6 +532,7 @@ int dymu_upload_plane(dymu_ctx* ctx, int plane, const double* host, size_t ld)
     if (plane == DYMU_PLANE_COST || plane == DYMU_PLANE_HAZARD_DENSITY
         || plane == DYMU_PLANE_TRAFFICABILITY)
         ctx->ceff_dirty = true;
+    if (plane == DYMU_PLANE_TOTAL_COST) ctx->solved = false;
     return DYMU_OK;
 }
 
@@ -667,6 +668,7 @@ int dymu_write_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t
     if (plane == DYMU_PLANE_COST || plane == DYMU_PLANE_HAZARD_DENSITY
         || plane == DYMU_PLANE_TRAFFICABILITY)
         ctx->ceff_dirty = true;
+    if (plane == DYMU_PLANE_TOTAL_COST) ctx->solved = false;  // no longer the solver's fixed point
     return DYMU_OK;
 }
 

@@ -164,6 +164,7 @@ class DyMuPathPlanner
     std::vector<base::Waypoint> localPathFromCell(long cell, base::Waypoint wInit);
     void localCellPose(long cell, double& gx, double& gy) const;
     double totalCostNoOffset(double x, double y);
+    long viewCell(localNode* n);
     void startReadback();
     void finishReadback();
 

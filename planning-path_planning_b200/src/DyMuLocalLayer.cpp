@@ -510,7 +510,7 @@ std::vector<base::Waypoint> DyMuPathPlanner::localPathFromCell(long cell, base::
 std::vector<base::Waypoint> DyMuPathPlanner::getLocalPath(localNode* lSetNode, base::Waypoint wInit, double)
 {
     if (!lSetNode) return std::vector<base::Waypoint>();
-    return localPathFromCell(lSetNode->window_cell, wInit);
+    return localPathFromCell(viewCell(lSetNode), wInit);
 }
 
 /*****************************PATH REPAIRING***********************************/

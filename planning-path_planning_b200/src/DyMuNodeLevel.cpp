@@ -159,11 +159,24 @@ void DyMuPathPlanner::createLocalMap(globalNode* gNode)
     ensureLocalWindow((double)i * global_res, (double)j * global_res, 0.0, 0.0, true);
 }
 
+// A local node view remembers the window cell it was filled from; the window may have grown or
+// moved since (dymu_local_reshape), so the cell is looked up again from the node's position.
+long DyMuPathPlanner::viewCell(localNode* n)
+{
+    if (!n || !dev || !local_ready) return -1;
+    int64_t cell = -1;
+    if (!deviceOk(dymu_local_cell_of(dev, n->global_pose.position[0], n->global_pose.position[1], &cell),
+                  "local node view"))
+        return -1;
+    n->window_cell = (long)cell;
+    return (long)cell;
+}
+
 // reference: L.cpp:979-1023 (no zero test: a flat neighbourhood yields NaN, L.cpp:1021-1022)
 void DyMuPathPlanner::gradientNode(localNode* nodeTarget, double& dnx, double& dny)
 {
     dnx = dny = std::numeric_limits<double>::quiet_NaN();
-    if (!nodeTarget || !dev || !local_ready || nodeTarget->window_cell < 0) return;
+    if (viewCell(nodeTarget) < 0) return;
     int64_t gx0, gy0;
     uint32_t wg, r;
     dymu_local_info(dev, &gx0, &gy0, &wg, &r);
@@ -191,7 +204,7 @@ void DyMuPathPlanner::gradientNode(localNode* nodeTarget, double& dnx, double& d
 // computeLocalPlanning.
 bool DyMuPathPlanner::isBlockingObstacle(localNode* obNode, uint& maxIndex, uint& minIndex)
 {
-    if (!obNode || !dev || !local_ready || obNode->window_cell < 0 || current_path.empty()) return false;
+    if (viewCell(obNode) < 0 || current_path.empty()) return false;
     std::vector<double> xy(current_path.size() * 2);
     for (size_t k = 0; k < current_path.size(); ++k)
     {
