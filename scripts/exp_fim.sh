@@ -1,7 +1,7 @@
 #!/bin/bash
-out=gpurun_out/exp_fim16.log
+out=gpurun_out/exp_fim18.log
 : > $out
-for R in 0 1 2 4; do
-    echo "=== refresh=$R" >> $out
-    DYMU_FIM_REFRESH=$R timeout 120 python scripts/probe_solve.py --n 4096 --reps 3 --check 2>&1 | grep "rep 2\|max rel" >> $out
+for B in 6 8 12; do
+    echo "=== tile64 band=$B" >> $out
+    DYMU_FIM_TILE=64 DYMU_FIM_BAND=$B DYMU_FIM_INNER=128 timeout 120 python scripts/probe_solve.py --n 4096 --reps 3 --nopath 2>&1 | grep "rep 2" >> $out
 done
