@@ -14,8 +14,9 @@
 //   k_blocking       isBlockingObstacle as a parallel min/max reduction (L.cpp:441-471)
 //   risk dilation    MODE 1 of the tiled FIM kernel (dymu_fim.cu)       (L.cpp:493-576)
 //   k_local_march    narrow-band march on `deviation` in the reference's exact pop order,
-//                    one warp: parallel argmin scan, order-preserving erase, the four
-//                    neighbour updates on four lanes                    (L.cpp:578-805)
+//                    two warps: order-preserving erase and the four neighbour updates on
+//                    four lanes of warp 0, the argmin scan of the band on warp 1 one pop
+//                    ahead                                              (L.cpp:578-805)
 //   k_local_path     single-warp gradient descent with Dijkstra fallback (L.cpp:807-1023)
 #include <stdlib.h>
 
@@ -321,6 +322,11 @@ struct MarchArgs
     const double* ltot_cache; // getTotalCost of every window cell (k_local_total_cost_cache)
     uint32_t prev_prop;      // nodes to reset from the previous call (L.cpp:589-599)
     uint64_t max_pops;
+    // per-axis tables the march fills before its first pop (everything in them depends on one
+    // window coordinate only): squared world distance to the end node per column / row
+    // (CONSERVATIVE key, L.cpp:735-741) and the node getNearestGlobalNode maps a parent to
+    double* axis_d2;         // [2 * w]: columns, then rows
+    int32_t* axis_node;      // [2 * wg]: columns, then rows; -1: no node
 };
 
 // getTotalCost(localNode*), L.cpp:473-491
@@ -350,6 +356,7 @@ __device__ __forceinline__ double local_total_cost(const LocalView& v, int64_t c
 //   * the array is compacted (stable) when it runs full or mostly holds tombstones.
 // Keys of live slots are finite, so +inf is free to mean "erased".
 constexpr uint32_t kBandSlots = 12288;
+static_assert(kBandSlots < (1u << 14), "k_local_march packs slot numbers into 14 bits");
 constexpr size_t kBandSmem = (size_t)kBandSlots * (sizeof(double) + sizeof(uint32_t));
 
 // 0: usable cell; -1: outside the global map (NULL in the reference); -2: outside the window
@@ -378,12 +385,24 @@ __device__ __forceinline__ int box_class(const MapBox& b, int X, int Y)
 }
 
 // world_pose (L.cpp:35-44) from window coordinates, same expression order as global_pose()
+__device__ __forceinline__ double world_axis(const LocalView& v, int64_t g0, uint32_t X)
+{
+    double px = (double)(g0 + X / v.r);
+    double lx = (double)(X % v.r), rr = (double)v.r;
+    return (px - 0.5 + (0.5 / rr) + lx * (1 / rr)) / v.gres;
+}
 __device__ __forceinline__ void world_xy(const LocalView& v, uint32_t X, uint32_t Y, double& wx, double& wy)
 {
-    double px = (double)(v.gx0 + X / v.r), py = (double)(v.gy0 + Y / v.r);
-    double lx = (double)(X % v.r), ly = (double)(Y % v.r), rr = (double)v.r;
-    wx = (px - 0.5 + (0.5 / rr) + lx * (1 / rr)) / v.gres;
-    wy = (py - 0.5 + (0.5 / rr) + ly * (1 / rr)) / v.gres;
+    wx = world_axis(v, v.gx0, X);
+    wy = world_axis(v, v.gy0, Y);
+}
+// one axis of getNearestGlobalNode (G.cpp:572-584) for node coordinate g: the node index or -1
+__device__ __forceinline__ int32_t nearest_node_axis(double gres, double g, uint32_t n)
+{
+    double f = g / gres + 0.5;
+    if (!(f >= 0.0) || !(f < 4294967296.0)) return -1;
+    uint32_t u = (uint32_t)f;
+    return u >= n ? -1 : (int32_t)u;
 }
 
 // propagateLocalNode's neighbour pair rule, L.cpp:705-717 (ca/cb: cell_class of the pair)
@@ -409,15 +428,112 @@ __global__ void k_local_total_cost_cache(LocalView v, double* cache)
     }
 }
 
-__global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
+// Two warps.  Warp 0 is the march: pop, erase, the four neighbour updates, push -- strictly in the
+// reference's order.  Warp 1 only looks for minima: as soon as warp 0 has announced which slot pop
+// k takes, warp 1 scans the band for the best of the REST (keys as they were before pop k touched
+// anything) while warp 0 updates the neighbours.  Keys only ever decrease and new entries only
+// appear at the tail, so the minimum for pop k+1 is the lexicographic (key, slot) minimum of that
+// "best of the rest" and the at most four entries pop k lowered or created -- which warp 0 holds
+// in registers.  The band scan, 40 % of a pop, leaves the critical path.
+constexpr unsigned long long kMarchExit = ~0ull;
+constexpr int kMarchSpinLimit = 1 << 26;  // a broken hand-shake ends the kernel instead of hanging it
+
+__global__ void __launch_bounds__(64, 1) k_local_march(MarchArgs a)
 {
     extern __shared__ double s_key[];                      // kBandSlots keys ...
     uint32_t* s_xy = (uint32_t*)(s_key + kBandSlots);      // ... and packed (Y << 16 | X) cells
+    // warp 0 -> warp 1, one word so that no fence is needed: slot popped [0,14), band head [14,28)
+    // and tail [28,42) as they were before the pop, pop number mod 2^22 above
+    __shared__ volatile unsigned long long s_pub;
+    __shared__ volatile uint32_t s_min_seq;                // scans finished by warp 1
+    __shared__ volatile unsigned long long s_mkey;         // its answer: bit pattern of the best key ...
+    __shared__ volatile uint32_t s_mslot;                  // ... and its slot
     const LocalView& v = a.v;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const double inf = DYMU_INF;
+    const unsigned long long kInfBits = 0x7FF0000000000000ull;
     const uint32_t w = v.w;
+    const uint32_t wg = w / v.r;
+    if (threadIdx.x == 0)
+    {
+        s_pub = 0;
+        s_min_seq = 0;
+        s_mkey = kInfBits;
+        s_mslot = 0xFFFFFFFFu;
+    }
+    int64_t status = DYMU_LOCAL_OK, end_cell = -1;
+    int64_t agent = cell_of(v, a.sx, a.sy);
+    int64_t node_end = -1;
+    double ex = 0, ey = 0;
+    if (agent < 0) status = DYMU_LOCAL_WINDOW_EXCEEDED;
+    else if (v.obst[cell_addr(v, agent)]) status = DYMU_LOCAL_START_IN_OBSTACLE;  // L.cpp:610-614
+    if (status == DYMU_LOCAL_OK && a.approach == 0)
+    {
+        node_end = cell_of(v, a.ox, a.oy);  // L.cpp:629
+        if (node_end < 0) status = DYMU_LOCAL_WINDOW_EXCEEDED;
+        else if (v.obst[cell_addr(v, node_end)]) status = DYMU_LOCAL_END_IN_OBSTACLE;
+        else world_pose(v, node_end, ex, ey);
+    }
+    // the per-axis tables (both warps)
+    int32_t* const node_x = a.axis_node;
+    int32_t* const node_y = a.axis_node + wg;
+    double* const d2_x = a.axis_d2;
+    double* const d2_y = a.axis_d2 + w;
+    if (status == DYMU_LOCAL_OK)
+    {
+        for (uint32_t q = threadIdx.x; q < wg; q += 64)
+        {
+            node_x[q] = nearest_node_axis(v.gres, (double)(v.gx0 + q), v.nx);
+            node_y[q] = nearest_node_axis(v.gres, (double)(v.gy0 + q), v.ny);
+        }
+        if (a.approach == 0)
+            for (uint32_t q = threadIdx.x; q < w; q += 64)
+            {
+                const double dx = world_axis(v, v.gx0, q) - ex, dy = world_axis(v, v.gy0, q) - ey;
+                d2_x[q] = dx * dx;
+                d2_y[q] = dy * dy;
+            }
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32)
+    {
+        // ---- warp 1: best of the rest for every announced pop
+        for (uint32_t k = 1;; ++k)
+        {
+            unsigned long long pub;
+            int spins = 0;
+            do pub = s_pub;
+            while (pub != kMarchExit && (uint32_t)(pub >> 42) != (k & 0x3FFFFFu) && ++spins < kMarchSpinLimit);
+            if (pub == kMarchExit || (uint32_t)(pub >> 42) != (k & 0x3FFFFFu)) return;
+            const uint32_t bp = (uint32_t)pub & 0x3FFFu, head = (uint32_t)(pub >> 14) & 0x3FFFu,
+                           tail = (uint32_t)(pub >> 28) & 0x3FFFu;
+            unsigned long long best = kInfBits;
+            uint32_t bslot = 0xFFFFFFFFu;
+#pragma unroll 4
+            for (uint32_t q = head + lane; q < tail; q += 32)
+            {
+                const unsigned long long kb = (unsigned long long)__double_as_longlong(s_key[q]);
+                if (kb < best && q != bp)
+                {
+                    best = kb;
+                    bslot = q;
+                }
+            }
+            const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+            const uint32_t mhi = __reduce_min_sync(full, hi);
+            const uint32_t mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xFFFFFFFFu);
+            const uint32_t ms = __reduce_min_sync(full, (hi == mhi && lo == mlo) ? bslot : 0xFFFFFFFFu);
+            if (lane == 0)
+            {
+                s_mkey = ((unsigned long long)mhi << 32) | mlo;
+                s_mslot = mhi >= 0x7FF00000u ? 0xFFFFFFFFu : ms;
+                __threadfence_block();
+                s_min_seq = k;
+            }
+            __syncwarp();
+        }
+    }
     const int64_t bx = v.gx0 * (int64_t)v.r, by = v.gy0 * (int64_t)v.r;
     // the global map in window coordinates, clamped just outside the window: all the
     // neighbour classification below is 32-bit compares
@@ -426,7 +542,10 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
     // floor(X / r) == umulhi(X, r_magic) for X, r < 2^16 (r == 1 would need 2^32: handled apart)
     const uint32_t r_magic = 0xFFFFFFFFu / v.r + 1;
     const bool r_is_one = v.r == 1;
-    const uint32_t wg = w / v.r;
+    // cells whose four neighbours are all inside the window and the map: no classification needed
+    const int ix0 = max(box.x0, 0) + 1, iy0 = max(box.y0, 0) + 1;
+    const unsigned ixs = (unsigned)max(min(box.x1, (int)w) - 1 - ix0, 0),
+                   iys = (unsigned)max(min(box.y1, (int)w) - 1 - iy0, 0);
     uint32_t* pos = a.nb;  // per window cell: slot of the node while it is in the band
     // reset of the previous propagation, L.cpp:589-599
     for (uint32_t q = lane; q < a.prev_prop; q += 32)
@@ -438,23 +557,10 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
         v.ltot[o] = inf;
     }
     __syncwarp();
-    int64_t status = DYMU_LOCAL_OK, end_cell = -1;
     uint64_t closed = 0;
     uint32_t head = 0, tail = 0, live = 0, prop_n = 0, nb_peak = 0;
-    int64_t agent = cell_of(v, a.sx, a.sy);
-    int64_t node_end = -1;
-    double ex = 0, ey = 0;
-    if (agent < 0) status = DYMU_LOCAL_WINDOW_EXCEEDED;
-    else if (v.obst[cell_addr(v, agent)]) status = DYMU_LOCAL_START_IN_OBSTACLE;  // L.cpp:610-614
     if (status == DYMU_LOCAL_OK)
     {
-        if (a.approach == 0)
-        {
-            node_end = cell_of(v, a.ox, a.oy);  // L.cpp:629
-            if (node_end < 0) status = DYMU_LOCAL_WINDOW_EXCEEDED;
-            else if (v.obst[cell_addr(v, node_end)]) status = DYMU_LOCAL_END_IN_OBSTACLE;
-            else world_pose(v, node_end, ex, ey);
-        }
         if (lane == 0)
         {
             size_t o = cell_addr(v, agent);
@@ -491,13 +597,34 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
 #endif
     bool end_ready = false, end_closed = false;
     int64_t end_addr = -1;  // lanes 0..3: the end node's neighbours, lane 4: the end node
+    // the band entries the previous pop lowered or created (lanes 0..3): (key bits, slot); before
+    // the first pop that is the agent's entry in slot 0
+    unsigned long long ev_key = kInfBits;
+    uint32_t ev_slot = 0xFFFFFFFFu;
+    if (status == DYMU_LOCAL_OK && lane == 0)
+    {
+        ev_key = (unsigned long long)__double_as_longlong(s_key[0]);
+        ev_slot = 0;
+    }
+    const int ndx = (lane == 2) - (lane == 1), ndy = (lane == 3) - (lane == 0);  // nb4 order, L.cpp:57-65
+    bool rescan = false;  // the slots were renumbered: this pop scans the band itself
+    auto wait_scan = [&](uint32_t k) -> bool {
+        int spins = 0;
+        while (s_min_seq < k)
+            if (++spins >= kMarchSpinLimit) return false;
+        return true;
+    };
     while (status == DYMU_LOCAL_OK)
     {
         if (live == 0) { status = DYMU_LOCAL_EXHAUSTED; break; }
         if (++pops > a.max_pops) { status = DYMU_LOCAL_EXHAUSTED; break; }
         // ---- housekeeping: stable compaction of the slot array
+        // warp 1's scan for the previous pop has to be finished before its answer is used -- and
+        // before the slots may be renumbered under it
+        if (!wait_scan((uint32_t)pops - 1)) { status = DYMU_LOCAL_EXHAUSTED; break; }
         if (tail + 4 > kBandSlots || tail - head > live + 64)
         {
+            rescan = true;
             uint32_t dst = 0;
             for (uint32_t base = head; base < tail; base += 32)
             {
@@ -523,20 +650,21 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
         }
         LM_MARK(0);
         // ---- minCostLocalNode: strict '<' argmin, earliest position wins (L.cpp:752-805)
-        double bk0 = inf;
-        uint32_t bp0 = 0xFFFFFFFFu;
-#pragma unroll 4
-        for (uint32_t q = head + lane; q < tail; q += 32)
-        {
-            double key = s_key[q];
-            if (key < bk0)
-            {
-                bk0 = key;
-                bp0 = q;
-            }
-        }
         uint32_t bp;
+        if (rescan)
         {
+            double bk0 = inf;
+            uint32_t bp0 = 0xFFFFFFFFu;
+#pragma unroll 4
+            for (uint32_t q = head + lane; q < tail; q += 32)
+            {
+                double key = s_key[q];
+                if (key < bk0)
+                {
+                    bk0 = key;
+                    bp0 = q;
+                }
+            }
             // lexicographic (key, slot) minimum over the lanes; keys are non-negative (or +inf
             // for "nothing"), so their bit patterns order like the values
             const unsigned long long kb = (unsigned long long)__double_as_longlong(bk0);
@@ -544,8 +672,29 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
             const uint32_t mhi = __reduce_min_sync(full, hi);
             const uint32_t mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xFFFFFFFFu);
             bp = __reduce_min_sync(full, (hi == mhi && lo == mlo) ? bp0 : 0xFFFFFFFFu);
+            rescan = false;
+        }
+        else
+        {
+            // best of the rest (warp 1, lane 4 here) against what the previous pop touched (lanes 0..3)
+            unsigned long long ck = lane < 4 ? ev_key : kInfBits;
+            uint32_t cs = lane < 4 ? ev_slot : 0xFFFFFFFFu;
+            if (lane == 4)
+            {
+                ck = s_mkey;
+                cs = s_mslot;
+            }
+            if (cs == 0xFFFFFFFFu) ck = kInfBits;
+            const uint32_t hi = (uint32_t)(ck >> 32), lo = (uint32_t)ck;
+            const uint32_t mhi = __reduce_min_sync(full, hi);
+            const uint32_t mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xFFFFFFFFu);
+            bp = __reduce_min_sync(full, (hi == mhi && lo == mlo) ? cs : 0xFFFFFFFFu);
+            if (mhi >= 0x7FF00000u) bp = 0xFFFFFFFFu;
         }
         if (bp == 0xFFFFFFFFu) { status = DYMU_LOCAL_EXHAUSTED; break; }
+        if (lane == 0)
+            s_pub = (unsigned long long)bp | ((unsigned long long)head << 14) | ((unsigned long long)tail << 28)
+                    | ((unsigned long long)((uint32_t)pops & 0x3FFFFFu) << 42);
         const uint32_t pxy = s_xy[bp];
         const int X = (int)(pxy & 0xffffu), Y = (int)(pxy >> 16);
         const size_t oX = (size_t)Y * v.pitch + X;
@@ -580,23 +729,34 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
         uint32_t lin = 0;
         bool is_end_candidate = false, is_new = false, lowered = false;
         double newkey = 0;
+        ev_key = kInfBits;
+        ev_slot = 0xFFFFFFFFu;
         if (lane < 5 && oX == (size_t)end_addr) end_closed = true;
         if (lane < 4)
         {
-            if (lane == 0) nY -= 1; else if (lane == 1) nX -= 1; else if (lane == 2) nX += 1; else nY += 1;
-            int cls = box_class(box, nX, nY);
+            nX += ndx;
+            nY += ndy;
+            int cls = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            if ((unsigned)(nX - ix0) >= ixs || (unsigned)(nY - iy0) >= iys)
+            {
+                cls = box_class(box, nX, nY);
+                c0 = box_class(box, nX, nY - 1);
+                c1 = box_class(box, nX - 1, nY);
+                c2 = box_class(box, nX + 1, nY);
+                c3 = box_class(box, nX, nY + 1);
+            }
             if (cls == -2) status = DYMU_LOCAL_WINDOW_EXCEEDED;
             if (cls == 0)
             {
                 o = (size_t)((uint32_t)nY * v.pitch + (uint32_t)nX);
                 lin = (uint32_t)nY * w + (uint32_t)nX;
-                const int c0 = box_class(box, nX, nY - 1), c1 = box_class(box, nX - 1, nY),
-                          c2 = box_class(box, nX + 1, nY), c3 = box_class(box, nX, nY + 1);
                 const uint8_t st = v.state[o], ob = v.obst[o];
                 const double d0 = (c0 == 0) ? v.dev[o - v.pitch] : inf, d1 = (c1 == 0) ? v.dev[o - 1] : inf,
                              d2 = (c2 == 0) ? v.dev[o + 1] : inf, d3 = (c3 == 0) ? v.dev[o + v.pitch] : inf;
                 const double R = v.risk[o], cur = v.dev[o], lt0 = v.ltot[o], ltc = a.ltot_cache[o];
                 const uint32_t slot = pos[lin];
+                double h2 = 0;  // CONSERVATIVE: squared distance to the end node, L.cpp:735-741
+                if (a.approach == 0) h2 = d2_x[nX] + d2_y[nY];
                 LM_MARK(4);
                 // L.cpp:658-663: looking at a neighbour under a different parent subdivides it
                 const uint32_t PX = r_is_one ? (uint32_t)X : __umulhi((uint32_t)X, r_magic),
@@ -605,10 +765,8 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
                                QY = r_is_one ? (uint32_t)nY : __umulhi((uint32_t)nY, r_magic);
                 if (QX != PX || QY != PY)
                 {
-                    int64_t gi, gj, pi, pj;
-                    if (global_node_of(v, (double)(v.gx0 + QX), (double)(v.gy0 + QY), gi, gj)
-                        && global_node_of(v, (double)(v.gx0 + PX), (double)(v.gy0 + PY), pi, pj)
-                        && (gi != pi || gj != pj))
+                    const int32_t gi = node_x[QX], gj = node_y[QY], pi = node_x[PX], pj = node_y[PY];
+                    if ((gi | gj | pi | pj) >= 0 && (gi != pi || gj != pj))
                     {
                         int64_t ex_ = gi - v.gx0, ey_ = gj - v.gy0;
                         if (ex_ >= 0 && ey_ >= 0 && ex_ < wg && ey_ < wg) a.entered[ey_ * wg + ex_] = 1;
@@ -636,13 +794,13 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
                             lowered = true;
                             v.dev[o] = Tn;
                             newkey = Tn;
-                            if (a.approach == 0)
+                            if (a.approach == 0) newkey = newkey + sqrt(h2);
+                            if (!is_new)
                             {
-                                double wx, wy;
-                                world_xy(v, (uint32_t)nX, (uint32_t)nY, wx, wy);
-                                newkey = newkey + sqrt((wx - ex) * (wx - ex) + (wy - ey) * (wy - ey));
+                                s_key[slot] = newkey;
+                                ev_slot = slot;
                             }
-                            if (!is_new) s_key[slot] = newkey;
+                            ev_key = (unsigned long long)__double_as_longlong(newkey);
                         }
                         is_end_candidate = (lt < a.t_overtake) && (R == 0);  // L.cpp:668-671
                     }
@@ -663,6 +821,7 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
             s_key[tail + off] = newkey;
             pos[lin] = tail + off;
             a.prop[prop_n + off] = lin;
+            ev_slot = tail + off;
         }
         tail += added;
         live += added;
@@ -703,6 +862,7 @@ __global__ void __launch_bounds__(32, 1) k_local_march(MarchArgs a)
     }
     if (lane == 0)
     {
+        s_pub = kMarchExit;  // releases warp 1
         a.result[0] = (status == DYMU_LOCAL_OK) ? end_cell : -1;
         a.result[1] = status;
         a.result[2] = (int64_t)closed;
@@ -974,6 +1134,8 @@ static int local_alloc(dymu_ctx* ctx, dymu_local& l, uint32_t wg)
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.first, (size_t)l.w * l.w * sizeof(uint32_t)));
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.prop, (size_t)l.nb_cap * sizeof(uint32_t)));
     DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.entered, (size_t)wg * wg));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.axis_d2, (size_t)2 * l.w * sizeof(double)));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&l.axis_node, (size_t)2 * wg * sizeof(int32_t)));
     uint32_t nt = l.pitch / tile;
     DYMU_TRY(dymu_internal_fim_alloc(ctx, &l.work, (size_t)nt * nt));
     l.allocated = true;
@@ -984,7 +1146,8 @@ static void local_release(dymu_local& l)
 {
     if (!l.allocated) return;
     dymu_internal_fim_free(&l.work);
-    void* ptrs[] = {l.risk, l.dev, l.ltot, l.crisk, l.obst, l.state, l.nb_idx, l.first, l.prop, l.entered};
+    void* ptrs[] = {l.risk, l.dev, l.ltot, l.crisk, l.obst, l.state, l.nb_idx, l.first, l.prop, l.entered,
+                    l.axis_d2, l.axis_node};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     memset(&l, 0, sizeof(l));
@@ -1267,6 +1430,8 @@ int dymu_local_propagate(dymu_ctx* ctx, int approach, double start_x, double sta
     a.max_pops = (uint64_t)l.w * l.w;
     // crisk is scratch between two risk dilations (dymu_local_expand_risk rebuilds it)
     a.ltot_cache = l.crisk;
+    a.axis_d2 = l.axis_d2;
+    a.axis_node = l.axis_node;
     {
         size_t cells = (size_t)l.w * l.w;
         uint32_t grid = (uint32_t)std::min<size_t>((cells + 255) / 256, (size_t)ctx->sm_count * 8);
@@ -1276,7 +1441,7 @@ int dymu_local_propagate(dymu_ctx* ctx, int approach, double start_x, double sta
     }
     DYMU_CUDA_TRY(ctx, cudaFuncSetAttribute(k_local_march, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)kBandSmem));
-    k_local_march<<<1, 32, kBandSmem, ctx->stream>>>(a);
+    k_local_march<<<1, 64, kBandSmem, ctx->stream>>>(a);
     ctx->launches++;
     DYMU_CUDA_TRY(ctx, cudaGetLastError());
     int64_t* h = (int64_t*)ctx->h_pinned;
