@@ -458,19 +458,25 @@ def headline_plan4096(args, D, pkg, affinity):
     dev.download_plane("cost", xform=pkg.cuda_api.XFORM_EFFECTIVE_COST, out=cost_host.numpy())
     t_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
 
+    # the matrix is page-locked: the solve kernel stores each tile into it as soon as the front
+    # is past the tile (dymu_set_total_cost_export), download_*_begin/_end then have nothing to copy
+    direct = dev.set_total_cost_export(t_host.numpy(), xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
+
     def plan_cabi():
-        dev.plan_streamed(cost_host.numpy(), goal)
+        st_ = dev.plan_streamed(cost_host.numpy(), goal)
         dev.download_total_cost_begin(t_host.numpy(), xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
         dev.extract_global_path(float(start[0]), float(start[1]), 0.4, goal[0], goal[1])
         dev.download_total_cost_end()
+        return st_
 
     for _ in range(min(2, args.warmup)):
         plan_cabi()
     D.barrier()
     dev.event_record(2)
     for _ in range(args.steps):
-        plan_cabi()
+        st_cabi = plan_cabi()
     dev.event_record(3)
+    dev.set_total_cost_export(None)
     cabi_ms = dev.event_elapsed_ms(2, 3)
     D.barrier()
     t_check = t_host.numpy().copy() if rank == 0 else None
@@ -595,11 +601,17 @@ def headline_plan4096(args, D, pkg, affinity):
                 "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + nwp * 32,
                 "api": "DyMuPathPlanner::setCostMap(const double*, ld) -> computeEntireTotalCostMap() -> "
                        "getPath() -> getTotalCostMatrix(double*, ld) through libdymu_b200.so, pinned "
-                       "host buffers, wall clock around the synchronous calls (max over ranks)"},
+                       "host buffers (the cost map is uploaded while the solve starts, the matrix is stored "
+                       "by the solve kernel tile by tile), wall clock around the synchronous calls (max "
+                       "over ranks)"},
         "e2e_cabi": {"value": world * 1e3 / (cabi_ms / args.steps), "unit": UNIT,
                      "ms_per_step": cabi_ms / args.steps,
-                     "api": "dymu_plan_streamed + dymu_download_total_cost_begin/_end + "
-                            "dymu_extract_global_path (include/dymu_cuda.h), CUDA events"},
+                     "api": "dymu_set_total_cost_export + dymu_plan_streamed + dymu_download_total_cost_begin/"
+                            "_end + dymu_extract_global_path (include/dymu_cuda.h), CUDA events",
+                     "matrix_delivery": {"direct": bool(direct),
+                                         "tiles_stored_during_solve": st_cabi["tiles_delivered_early"],
+                                         "tiles_stored_after_last_phase": st_cabi["tiles_delivered_late"],
+                                         "solve_kernel_ms": st_cabi["kernel_ms"]}},
         "link_gbs_per_rank": [{"h2d": r[0], "d2h": r[1]} for r in rates],
         "gpu_launches": int(launches),
         "clocks": clocks,

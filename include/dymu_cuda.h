@@ -72,8 +72,11 @@ typedef struct dymu_solve_stats
     float reset_ms;             /* device time of the total-cost reset */
     uint32_t goal_obstacle;     /* goals that sit on an obstacle cell and were therefore not seeded
                                    ("The goal is not valid", G.cpp:370-374) */
-    uint32_t reserved_;
+    uint32_t tiles_delivered_early; /* direct delivery (dymu_set_total_cost_export): tiles stored to the
+                                       caller's matrix while the solve was still running ... */
     uint64_t cells_written;     /* cells whose value was stored back to the plane (8 B each) */
+    uint32_t tiles_delivered_late;  /* ... and tiles stored after the last phase */
+    uint32_t reserved_;
 } dymu_solve_stats;
 
 /* ---- context ---------------------------------------------------------- */
@@ -217,6 +220,17 @@ int dymu_download_total_cost(dymu_ctx* ctx, uint32_t slot, double* host, size_t 
  * downloads another transformed plane; _end waits for the copy.  `host` should be pinned
  * memory, otherwise the copy is not asynchronous. */
 int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform);
+/* Direct delivery of getTotalCostMatrix (G.cpp:799-811): from now on every full single-goal solve
+ * (dymu_solve_total_cost, dymu_plan_streamed, dymu_solve_incremental when it solves from scratch)
+ * stores the total-cost matrix into `host` (row stride `ld` doubles) itself -- each tile as soon as
+ * the wave front is past it, the rest right after the last phase -- instead of leaving it to a
+ * copy afterwards; a later dymu_download_total_cost[_begin] with the same host / ld / xform then
+ * has nothing left to copy.  `host` must be page-locked memory the device can write to
+ * (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned tensor); otherwise nothing is set up and
+ * *direct comes back 0 (not an error).  The buffer is written during the solve and is only
+ * meaningful after a solve that returned DYMU_OK.  host == NULL switches it off.
+ * xform: DYMU_XFORM_NONE or DYMU_XFORM_INF_TO_MINUS1. */
+int dymu_set_total_cost_export(dymu_ctx* ctx, double* host, size_t ld, int xform, int* direct);
 int dymu_download_total_cost_end(dymu_ctx* ctx);
 /* values of a plane at n cells (k = j*nx+i), for getTotalCost(Waypoint) G.cpp:860-890 */
 int dymu_read_cells(dymu_ctx* ctx, int plane, uint32_t slot, const uint32_t* cell_index,

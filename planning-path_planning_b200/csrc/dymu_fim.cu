@@ -106,7 +106,18 @@ struct Params
     int phase_budget, min_slice;  // sweeps a CTA may spend per phase; smallest slice worth a tile load
     int outer0;                 // rotation of the three lists at entry (phase-bounded solves)
     double band;                // tiles with key > min key + band wait (inf = plain FIM)
+    // direct delivery (MODE 0, one problem).  tmax[tile]: bit pattern of an upper bound of the tile's
+    // values as of its last write-back, +inf while a passable cell is unreached, kExported once the
+    // tile has been stored to xout.  A tile whose bound lies below the smallest pending key can no
+    // longer change (the update is upwind: whatever a pending change produces is larger than it).
+    unsigned long long* tmax;   // nullptr: not tracked
+    double* xout;               // page-locked host matrix as the device sees it; nullptr: no delivery
+    size_t xld;
+    uint32_t xnx, xny;          // logical size (the plane is padded to whole tiles)
+    int xminus1;                // +inf is delivered as -1 (getTotalCostMatrix, G.cpp:799-811)
+    uint32_t xcap;              // tiles one CTA delivers per phase at most (<= 64)
 };
+constexpr unsigned long long kExported = 0xFFFFFFFFFFFFFFFFull;
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
 {
@@ -137,6 +148,28 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& phase)
         __threadfence();
         uint32_t target = (phase + 1) * gridDim.x;
         atomicAdd(counter, 1u);
+        while (ld_volatile_u32(counter) < target) { }
+        __threadfence();
+    }
+    phase++;
+    __syncthreads();
+}
+
+// the same barrier in two halves, so that a CTA can do work nobody waits for in between
+__device__ __forceinline__ void grid_barrier_arrive(uint32_t* counter, uint32_t phase, uint32_t* order)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        *order = atomicAdd(counter, 1u) - phase * gridDim.x;  // how many CTAs arrived before this one
+    }
+}
+__device__ __forceinline__ void grid_barrier_wait(uint32_t* counter, uint32_t& phase)
+{
+    if (threadIdx.x == 0)
+    {
+        uint32_t target = (phase + 1) * gridDim.x;
         while (ld_volatile_u32(counter) < target) { }
         __threadfence();
     }
@@ -225,6 +258,9 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     __shared__ uint32_t edge_mask;  // tile edges with a changed cell: 1 top, 2 bottom, 4 left, 8 right
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_emin[5];  // min changed value per edge [0..3], overall [4]
+    __shared__ uint32_t s_tmax;                // high word (rounded up) of the largest passable value
+    __shared__ uint32_t s_xn, s_xlist[64];     // tiles this CTA delivers in the current phase
+    __shared__ uint32_t s_xorder;              // its order of arrival at the barrier
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_per_prob = p.ntx * p.nty;
@@ -271,6 +307,22 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     auto sel3 = [](uint32_t* a, uint32_t* b, uint32_t* c, int k) { return k == 0 ? a : (k == 1 ? b : c); };
     auto sel3k = [](unsigned long long* a, unsigned long long* b, unsigned long long* c, int k) {
         return k == 0 ? a : (k == 1 ? b : c);
+    };
+    // direct delivery: one tile of the plane to the caller's matrix
+    auto deliver_tile = [&](uint32_t t) {
+        const uint32_t ty = t / p.ntx, tx = t - ty * p.ntx;
+#pragma unroll
+        for (int k = 0; k < K::CPT; ++k)
+        {
+            const int e = tid + k * K::THREADS;
+            const uint32_t gy = ty * TILE + e / TILE, gx = tx * TILE + e % TILE;
+            if (gx < p.xnx && gy < p.xny)
+            {
+                double v = __ldcg(&p.T[(size_t)gy * p.pitch + gx]);
+                if (p.xminus1 && v == DYMU_INF) v = -1.0;
+                p.xout[(size_t)gy * p.xld + gx] = v;
+            }
+        }
     };
     uint32_t phase = 0;
     unsigned long long n_tiles = 0, n_visits = 0, n_deferred = 0, n_inner = 0;
@@ -445,7 +497,11 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 flag_cur[tile_id] = 0;  // consumed; writers use flag_nxt / key_nxt this phase
                 key_cur[tile_id] = kNoKey;
             }
-            if (tid == 0) edge_mask = 0;
+            if (tid == 0)
+            {
+                edge_mask = 0;
+                s_tmax = 0;
+            }
             if (tid < 5) s_emin[tid] = kNoKey;
             __syncthreads();
             PC_MARK(pc_load)
@@ -536,6 +592,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 #endif
 
             // ---- write back changed cells and wake the neighbours whose halo went stale
+            uint32_t vmax = 0;  // direct delivery: high word, rounded up, of the largest passable value
             {
                 // smallest new value per tile edge = the priority the neighbour gets; [4]: smallest
                 // new value anywhere, the tile's own priority when it has to be continued
@@ -547,6 +604,8 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     int e = tid + k * K::THREADS;
                     int y = e / TILE, x = e % TILE;
                     double v = Ts[(y + 1) * P + x + 1];
+                    if (MODE == 0 && p.tmax && Cs[y * P + x] < DYMU_INF)
+                        vmax = max(vmax, (uint32_t)(key_of(v) >> 32) + 1u);
                     if (v != told[k])
                     {
                         n_written++;
@@ -583,6 +642,11 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                     }
                 }
             }
+            if (MODE == 0 && p.tmax)
+            {
+                vmax = __reduce_max_sync(0xffffffffu, vmax);
+                if (lane == 0 && vmax) atomicMax(&s_tmax, vmax);
+            }
             // No fence here: the values and the wake-ups are consumed after the grid barrier,
             // whose arrival (bar.sync, then thread 0's cumulative fence) orders them; tiles that
             // read this one's cells during the same phase may see old or new values, both are
@@ -600,6 +664,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 if (tid == 2 && (em & 4u) && tx > 0) { target = tile_id - 1; bit = kHaloRight; }
                 if (tid == 3 && (em & 8u) && tx + 1 < p.ntx) { target = tile_id + 1; bit = kHaloLeft; }
                 if (tid == 4 && more) { target = tile_id; bit = kResume; }  // cap hit: not converged
+                if (MODE == 0 && tid == 4 && p.tmax) p.tmax[tile_id] = (unsigned long long)s_tmax << 32;
                 if (target != 0xffffffffu)
                 {
                     unsigned long long kb = (MODE == 0) ? s_emin[tid] : 0ull;
@@ -637,7 +702,42 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             p.ctrl[3 + old] = 0;  // and its cursor
             p.gmin[old] = kNoKey;
         }
-        grid_barrier(&p.ctrl[6], phase);
+        if (MODE == 0 && p.xout)
+        {
+            // Between arriving at the barrier and leaving it, the CTAs that arrive in the first half
+            // -- they would only wait -- look through the tile bounds (a share of the array each,
+            // by order of arrival) and deliver the tiles the front has left behind.  The CTAs the
+            // others are waiting for skip this, so a phase is not made longer.
+            grid_barrier_arrive(&p.ctrl[6], phase, &s_xorder);
+            if (tid == 0) s_xn = 0;
+            // the smallest key that was pending when this phase began (nothing writes gmin[cur]
+            // during its own phase): every value below it is final
+            const unsigned long long gm = ld_volatile_u64(&p.gmin[cur]);
+            __syncthreads();
+            const uint32_t order = s_xorder, sharers = max(gridDim.x / 2u, 1u);
+            if (order < sharers)
+            {
+                const uint32_t per = (tiles_per_prob + sharers - 1) / sharers;
+                const uint32_t t_end = min((order + 1) * per, tiles_per_prob);
+                for (uint32_t t = order * per + tid; t < t_end; t += K::THREADS)
+                    if (ld_volatile_u64(&p.tmax[t]) < gm)
+                    {
+                        const uint32_t q = atomicAdd(&s_xn, 1u);
+                        if (q < p.xcap)  // the rest is found again next phase
+                        {
+                            s_xlist[q] = t;
+                            p.tmax[t] = kExported;
+                        }
+                    }
+                __syncthreads();
+                const uint32_t n = min(s_xn, p.xcap);
+                for (uint32_t q = 0; q < n; ++q) deliver_tile(s_xlist[q]);
+                if (tid == 0 && n) atomicAdd(&p.stats[7], (unsigned long long)n);
+            }
+            grid_barrier_wait(&p.ctrl[6], phase);
+        }
+        else
+            grid_barrier(&p.ctrl[6], phase);
         PC_MARK(pc_barrier)
     }
 #ifdef DYMU_FIM_PROFILE
@@ -670,6 +770,33 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     }
 }
 
+
+// Direct delivery, the rest: what the solve kernel did not get to store into the caller's matrix --
+// the tiles the front reached last and the ones it never reached.  Runs on the copy stream right
+// behind a converged solve, next to whatever the caller does then (path extraction).
+__global__ void __launch_bounds__(512) k_deliver_rest(const double* T, uint32_t pitch, uint32_t ntx, uint32_t nty,
+                                                      unsigned long long* tmax, double* xout, size_t xld,
+                                                      uint32_t xnx, uint32_t xny, int xminus1,
+                                                      unsigned long long* stats)
+{
+    if (ld_volatile_u64(&stats[3]) == 0) return;  // not converged: the plane is not final
+    const uint32_t total = ntx * nty;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x)
+    {
+        if (ld_volatile_u64(&tmax[t]) == kExported) continue;
+        const uint32_t ty = t / ntx, tx = t - ty * ntx;
+        for (uint32_t e = threadIdx.x; e < 32 * 32; e += blockDim.x)
+        {
+            const uint32_t gy = ty * 32 + e / 32, gx = tx * 32 + e % 32;
+            if (gx < xnx && gy < xny)
+            {
+                double v = __ldcg(&T[(size_t)gy * pitch + gx]);
+                if (xminus1 && v == DYMU_INF) v = -1.0;
+                xout[(size_t)gy * xld + gx] = v;
+            }
+        }
+    }
+}
 
 // One thread seeds all goals (there are at most a few hundred).  A goal on an obstacle cell is not
 // seeded and counted in stats[15]: "The goal is not valid", G.cpp:370-374 / 447-451.
@@ -873,6 +1000,7 @@ int dymu_internal_fim_reset(dymu_ctx* ctx, dymu_fim_work* w);
 int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_stats* stats)
 {
     if (L.tile != 32) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unsupported tile edge %d", L.tile);
+    DYMU_TRY(dymu_internal_settle_delivery(ctx));
     if (L.resume && L.work->pending)
     {
         // continue with the lists the previous launch left behind; new seeds are merged in
@@ -970,6 +1098,27 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     }
     prm.ctrl = w->ctrl;
     prm.stats = w->stats;
+    prm.tmax = nullptr;
+    prm.xout = nullptr;
+    prm.xld = 0;
+    prm.xnx = ctx->nx;
+    prm.xny = ctx->ny;
+    prm.xminus1 = ctx->export_xform == DYMU_XFORM_INF_TO_MINUS1;
+    // One tile per CTA and phase keeps the delivery inside the time an early CTA would wait at the
+    // barrier anyway (4096^2: solve 7.82 ms without, 7.90 ms with; 8.28 ms at 64 per phase); the
+    // half of the grid that delivers still moves 148 tiles per phase, twice what finishes.
+    prm.xcap = 1;
+    if (const char* e = getenv("DYMU_EXPORT_CAP"))
+        if (atoi(e) > 0 && atoi(e) <= 64) prm.xcap = (uint32_t)atoi(e);
+    if (L.mode == 0 && L.nprob == 1 && L.T == ctx->T && ctx->tile_tmax && (L.track_final || L.export_now))
+    {
+        prm.tmax = ctx->tile_tmax;
+        if (L.export_now && ctx->export_dev)
+        {
+            prm.xout = ctx->export_dev;
+            prm.xld = ctx->export_ld;
+        }
+    }
     prm.band = L.band;
     prm.inner_cap = ctx->fim_inner_cap;
     prm.phase_budget = ctx->fim_phase_budget > 0 ? ctx->fim_phase_budget : 1 << 30;
@@ -988,6 +1137,19 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     rc = (L.mode == 0) ? launch_fim<32, 0>(ctx, prm, total_tiles) : launch_fim<32, 1>(ctx, prm, total_tiles);
     DYMU_TRY(rc);
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+    if (prm.xout)
+    {
+        // the tiles that are left go out on the copy stream, beside whatever follows on the main one
+        DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev2, 0));
+        const uint32_t nt = L.ntx * L.nty;
+        const uint32_t g = nt < (uint32_t)ctx->sm_count * 2 ? nt : (uint32_t)ctx->sm_count * 2;
+        k_deliver_rest<<<g, 512, 0, ctx->copy_stream>>>(prm.T, prm.pitch, prm.ntx, prm.nty, prm.tmax, prm.xout,
+                                                        prm.xld, prm.xnx, prm.xny, prm.xminus1, prm.stats);
+        ctx->launches++;
+        DYMU_CUDA_TRY(ctx, cudaGetLastError());
+        DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tail, ctx->copy_stream));
+        ctx->export_tail_pending = true;
+    }
     unsigned long long h[16];
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, w->stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1038,8 +1200,13 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
         stats->inner_iterations = h[5];
         stats->goal_obstacle = (uint32_t)h[15];
         stats->cells_written = h[6];
+        stats->tiles_delivered_early = (uint32_t)h[7];
+        // (k_deliver_rest is still running: counted from here)
+        const uint32_t nt_all = L.ntx * L.nty;
+        stats->tiles_delivered_late = (prm.xout && h[3] && nt_all > h[7]) ? nt_all - (uint32_t)h[7] : 0;
         DYMU_CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev1, ctx->ev2));
     }
+    if (prm.xout && h[3]) ctx->export_done = true;  // the tail ran: the caller's matrix is complete
     w->rot = (int)((prm.outer0 + h[2]) % 3);
     w->pending = !h[3];
     w->unclean = !h[3];
@@ -1130,6 +1297,7 @@ static int solve_total_cost_impl(dymu_ctx* ctx, uint32_t n_goals, const uint32_t
     for (uint32_t q = 0; q < n_goals; ++q)
         if (goal_i[q] >= ctx->nx || goal_j[q] >= ctx->ny) DYMU_FAIL(ctx, DYMU_ERR_ARG, "goal %u outside the grid", q);
     DYMU_TRY(dymu_internal_refresh_ceff(ctx));
+    DYMU_TRY(dymu_internal_settle_delivery(ctx));
     size_t n = (size_t)ctx->pitch * ctx->rows;
     // resetTotalCostMap, G.cpp:473-485 (whole plane instead of the propagated-node list)
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1150,6 +1318,25 @@ static int solve_total_cost_impl(dymu_ctx* ctx, uint32_t n_goals, const uint32_t
     L.seed_kind = 0; L.seed_data = (const uint32_t*)ctx->d_scratch;
     L.goal_obst = ctx->obst;
     L.max_phases = max_phases;
+    ctx->export_done = false;
+    if (ctx->export_dev && n_goals == 1)
+    {
+        // direct delivery: every tile starts as "not finished" (+inf)
+        const size_t nt = (size_t)ctx->ntx * ctx->nty;
+        if (ctx->tile_tmax_cap < nt)
+        {
+            if (ctx->tile_tmax) cudaFree(ctx->tile_tmax);
+            ctx->tile_tmax = nullptr;
+            ctx->tile_tmax_cap = 0;
+            DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&ctx->tile_tmax, nt * sizeof(unsigned long long)));
+            ctx->tile_tmax_cap = nt;
+        }
+        DYMU_TRY(dymu_internal_fill(ctx, (double*)ctx->tile_tmax, 1.0 / 0.0, nt));
+        L.track_final = true;
+        // a phase-bounded launch is the head of a streamed solve: cost rows are still missing, and
+        // values that look finished may still drop when they arrive
+        L.export_now = (max_phases == 0);
+    }
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     int rc = dymu_internal_fim_run(ctx, L, &local);
@@ -1192,9 +1379,11 @@ int dymu_solve_start(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t m
 }
 
 static int solve_resume_impl(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges, bool keep_pending,
-                             double seed_key, uint32_t max_phases, dymu_solve_stats* stats)
+                             double seed_key, uint32_t max_phases, dymu_solve_stats* stats,
+                             bool deliver = false)
 {
     if (!ctx || (!ranges && n_ranges)) return DYMU_ERR_ARG;
+    if (!deliver) ctx->export_done = false;
     if (!ctx->have_cost) DYMU_FAIL(ctx, DYMU_ERR_STATE, "no cost map");
     if (n_ranges == 0 && !(keep_pending && ctx->work.pending))
     {
@@ -1243,6 +1432,8 @@ static int solve_resume_impl(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_r
     L.resume = keep_pending;
     L.max_phases = max_phases;
     L.seed_key = seed_key;
+    // the tail of a streamed solve: the whole cost map is there now (tile bounds were tracked by the head)
+    L.track_final = L.export_now = deliver && ctx->export_dev && ctx->tile_tmax && max_phases == 0;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     rc = dymu_internal_fim_run(ctx, L, &local);
@@ -1349,7 +1540,7 @@ static int solve_streamed(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint3
         return DYMU_OK;
     }
     if (n_ranges || !first.converged)
-        rc = solve_resume_impl(ctx, ranges, n_ranges, true, 0.0, 0, &rest);
+        rc = solve_resume_impl(ctx, ranges, n_ranges, true, 0.0, 0, &rest, true);
     else
         rest.converged = 1;
     if (stats)
@@ -1362,6 +1553,8 @@ static int solve_streamed(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint3
         stats->tiles_deferred += rest.tiles_deferred;
         stats->inner_iterations += rest.inner_iterations;
         stats->cells_written += rest.cells_written;
+        stats->tiles_delivered_early = rest.tiles_delivered_early;
+        stats->tiles_delivered_late = rest.tiles_delivered_late;
         stats->kernel_ms += rest.kernel_ms;
     }
     ctx->solved = (rc == DYMU_OK);
@@ -1381,7 +1574,9 @@ int dymu_reset_total_cost(dymu_ctx* ctx)
 {
     DYMU_GUARD(ctx);
     if (!ctx) return DYMU_ERR_ARG;
+    DYMU_TRY(dymu_internal_settle_delivery(ctx));
     ctx->solved = false;
+    ctx->export_done = false;
     ctx->work.pending = false;
     return dymu_internal_fill(ctx, ctx->T, 1.0 / 0.0, (size_t)ctx->pitch * ctx->rows);
 }
@@ -1407,6 +1602,7 @@ static int import_rows_impl(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t 
     if (!ctx || !src || !changed || slot >= ctx->n_slots || n_rows == 0
         || (uint64_t)j0 + n_rows > ctx->ny)
         return DYMU_ERR_ARG;
+    DYMU_TRY(dymu_internal_settle_delivery(ctx));
     size_t bytes = (size_t)ctx->nx * n_rows * sizeof(double);
     DYMU_TRY(dymu_internal_scratch(ctx, bytes + 64, device_ptr ? 64 : bytes + 64));
     int* d_flag = (int*)ctx->d_scratch;
@@ -1433,7 +1629,7 @@ static int import_rows_impl(dymu_ctx* ctx, uint32_t slot, uint32_t j0, uint32_t 
     DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_flag, 16, cudaMemcpyDeviceToHost, ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *changed = (int)(h[0] & 0xffffffffu);
-    if (*changed) ctx->solved = false;  // the plane moved away from the last solve's fixed point
+    if (*changed) ctx->solved = ctx->export_done = false;  // the plane moved away from the last solve's fixed point
     if (min_lowered)
     {
         long long bits = (long long)h[1];

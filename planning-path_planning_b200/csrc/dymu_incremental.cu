@@ -176,6 +176,7 @@ int dymu_solve_incremental(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, dymu
                           && n < ((size_t)1 << 32);
     if (!reusable) return dymu_solve_total_cost(ctx, 1, &goal_i, &goal_j, stats);
     if (stats) memset(stats, 0, sizeof(*stats));
+    // (an unchanged map keeps a matrix that was delivered directly; a partial re-solve does not)
     if (!ctx->ceff_dirty)
     {
         // nothing entered C_eff since the resident map was solved: it still is the answer
@@ -190,6 +191,7 @@ int dymu_solve_incremental(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, dymu
         DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&ctx->inc_visited, cap * sizeof(uint32_t)));
         ctx->inc_cap = (uint32_t)cap;
     }
+    ctx->export_done = false;
     dymu_fim_work* w = &ctx->work;
     DYMU_TRY(dymu_internal_fim_reset(ctx, w));
     w->rot = 0;

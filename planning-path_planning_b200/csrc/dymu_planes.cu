@@ -424,6 +424,7 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_part, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming));
+    DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev2));
@@ -456,12 +457,13 @@ int dymu_destroy(dymu_ctx* ctx)
     if (!ctx) return DYMU_OK;
     DYMU_GUARD(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     dymu_internal_local_free(ctx);
     dymu_internal_incremental_free(ctx);
     dymu_internal_fim_free(&ctx->work);
     void* ptrs[] = {ctx->elev, ctx->slope, ctx->raw, ctx->cost, ctx->haz, ctx->traff, ctx->ceff,
                     ctx->T, ctx->terrain, ctx->obst, ctx->locmode, ctx->d_lut, ctx->d_slopes,
-                    ctx->d_stage, ctx->d_scratch};
+                    ctx->d_stage, ctx->d_scratch, ctx->tile_tmax};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -473,6 +475,7 @@ int dymu_destroy(dymu_ctx* ctx)
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
     if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
+    if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
@@ -525,6 +528,7 @@ int dymu_upload_plane(dymu_ctx* ctx, int plane, const double* host, size_t ld)
     if (!ctx || !host || ld < ctx->nx) return DYMU_ERR_ARG;
     double* d = plane_ptr(ctx, plane);
     if (!d) DYMU_FAIL(ctx, DYMU_ERR_ARG, "unknown plane %d", plane);
+    if (plane == DYMU_PLANE_TOTAL_COST) DYMU_TRY(dymu_internal_settle_delivery(ctx));
     DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(d, ctx->pitch * sizeof(double), host, ld * sizeof(double),
                                          ctx->nx * sizeof(double), ctx->ny, cudaMemcpyHostToDevice,
                                          ctx->stream));
@@ -532,7 +536,7 @@ int dymu_upload_plane(dymu_ctx* ctx, int plane, const double* host, size_t ld)
     if (plane == DYMU_PLANE_COST || plane == DYMU_PLANE_HAZARD_DENSITY
         || plane == DYMU_PLANE_TRAFFICABILITY)
         ctx->ceff_dirty = true;
-    if (plane == DYMU_PLANE_TOTAL_COST) ctx->solved = false;
+    if (plane == DYMU_PLANE_TOTAL_COST) ctx->solved = ctx->export_done = false;
     return DYMU_OK;
 }
 
@@ -592,10 +596,53 @@ int dymu_download_plane(dymu_ctx* ctx, int plane, double* host, size_t ld, int x
     return download_f64(ctx, d, host, ld, xform);
 }
 
+// the solve itself stored the matrix there (dymu_set_total_cost_export)
+static bool already_delivered(const dymu_ctx* ctx, uint32_t slot, const double* host, size_t ld, int xform)
+{
+    return ctx->export_done && slot == 0 && host == ctx->export_host && ld == ctx->export_ld
+           && xform == ctx->export_xform;
+}
+
+int dymu_set_total_cost_export(dymu_ctx* ctx, double* host, size_t ld, int xform, int* direct)
+{
+    DYMU_GUARD(ctx);
+    if (!ctx) return DYMU_ERR_ARG;
+    if (direct) *direct = 0;
+    DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));  // a delivery that is still running
+    ctx->export_tail_pending = false;
+    ctx->export_host = ctx->export_dev = nullptr;
+    ctx->export_done = false;
+    if (!host) return DYMU_OK;
+    if (ld < ctx->nx || (xform != DYMU_XFORM_NONE && xform != DYMU_XFORM_INF_TO_MINUS1)) return DYMU_ERR_ARG;
+    // page-locked and mapped?  Both ends of the matrix are asked: a buffer that is only partly
+    // registered is no use
+    cudaPointerAttributes lo, hi;
+    const double* last = host + (size_t)(ctx->ny - 1) * ld + (ctx->nx - 1);
+    if (cudaPointerGetAttributes(&lo, host) != cudaSuccess || cudaPointerGetAttributes(&hi, last) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return DYMU_OK;
+    }
+    if (lo.type != cudaMemoryTypeHost || hi.type != cudaMemoryTypeHost || !lo.devicePointer || !hi.devicePointer
+        || (const char*)hi.devicePointer - (const char*)lo.devicePointer != (const char*)last - (const char*)host)
+        return DYMU_OK;
+    ctx->export_host = host;
+    ctx->export_dev = (double*)lo.devicePointer;
+    ctx->export_ld = ld;
+    ctx->export_xform = xform;
+    if (direct) *direct = 1;
+    return DYMU_OK;
+}
+
 int dymu_download_total_cost(dymu_ctx* ctx, uint32_t slot, double* host, size_t ld, int xform)
 {
     DYMU_GUARD(ctx);
     if (!ctx || !host || ld < ctx->nx || slot >= ctx->n_slots) return DYMU_ERR_ARG;
+    if (already_delivered(ctx, slot, host, ld, xform))
+    {
+        DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));  // k_deliver_rest
+        return DYMU_OK;
+    }
     return download_f64(ctx, ctx->T + (size_t)slot * ctx->pitch * ctx->rows, host, ld, xform);
 }
 
@@ -603,6 +650,7 @@ int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, s
 {
     DYMU_GUARD(ctx);
     if (!ctx || !host || ld < ctx->nx || slot >= ctx->n_slots) return DYMU_ERR_ARG;
+    if (already_delivered(ctx, slot, host, ld, xform)) return DYMU_OK;
     if (xform != DYMU_XFORM_NONE) DYMU_TRY(ensure_stage(ctx));  // allocate before forking
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
@@ -660,6 +708,7 @@ int dymu_write_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t
     if (!ctx || !host || !rect_ok(ctx, i0, j0, w, h)) return DYMU_ERR_ARG;
     double* d = plane_ptr(ctx, plane);
     if (!d) return DYMU_ERR_ARG;
+    if (plane == DYMU_PLANE_TOTAL_COST) DYMU_TRY(dymu_internal_settle_delivery(ctx));
     DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(d + (size_t)j0 * ctx->pitch + i0,
                                          ctx->pitch * sizeof(double), host, w * sizeof(double),
                                          w * sizeof(double), h, cudaMemcpyHostToDevice,
@@ -668,7 +717,7 @@ int dymu_write_rect(dymu_ctx* ctx, int plane, uint32_t i0, uint32_t j0, uint32_t
     if (plane == DYMU_PLANE_COST || plane == DYMU_PLANE_HAZARD_DENSITY
         || plane == DYMU_PLANE_TRAFFICABILITY)
         ctx->ceff_dirty = true;
-    if (plane == DYMU_PLANE_TOTAL_COST) ctx->solved = false;  // no longer the solver's fixed point
+    if (plane == DYMU_PLANE_TOTAL_COST) ctx->solved = ctx->export_done = false;  // no longer the solver's fixed point
     return DYMU_OK;
 }
 

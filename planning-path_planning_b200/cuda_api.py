@@ -37,11 +37,12 @@ class SolveStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_uint32), ("converged", C.c_uint32),
                 ("tile_activations", C.c_uint64), ("cell_updates", C.c_uint64),
                 ("cells_reached", C.c_uint64), ("tiles_deferred", C.c_uint64), ("inner_iterations", C.c_uint64), ("kernel_ms", C.c_float), ("reset_ms", C.c_float),
-                ("goal_obstacle", C.c_uint32), ("reserved_", C.c_uint32),
-                ("cells_written", C.c_uint64)]
+                ("goal_obstacle", C.c_uint32), ("tiles_delivered_early", C.c_uint32),
+                ("cells_written", C.c_uint64),
+                ("tiles_delivered_late", C.c_uint32), ("reserved_", C.c_uint32)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved_"}
 
 
 _SIG = {
@@ -100,6 +101,7 @@ _SIG = {
     "dymu_download_total_cost": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_size_t, C.c_int]),
     "dymu_download_total_cost_begin": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_size_t, C.c_int]),
     "dymu_download_total_cost_end": (C.c_int, [C.c_void_p]),
+    "dymu_set_total_cost_export": (C.c_int, [C.c_void_p, _dp, C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
     "dymu_read_cells": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, _u32p, C.c_uint32, _dp]),
     "dymu_read_node": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _dp]),
     "dymu_count_leq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_double, C.POINTER(C.c_uint64)]),
@@ -398,6 +400,18 @@ class DeviceLayer:
         is valid after download_total_cost_end()."""
         self._chk(self._l.dymu_download_total_cost_begin(self._h, slot, out.ctypes.data_as(_dp),
                                                          out.shape[1], xform))
+
+    def set_total_cost_export(self, out, xform=XFORM_NONE):
+        """Direct delivery: full single-goal solves store the total-cost matrix into `out` (a pinned,
+        C-contiguous float64 array, e.g. the numpy view of a torch pinned tensor) while they run.
+        Returns False when `out` is not page-locked (nothing is set up then); None switches it off."""
+        direct = C.c_int(0)
+        if out is None:
+            self._chk(self._l.dymu_set_total_cost_export(self._h, None, 0, xform, C.byref(direct)))
+            return False
+        self._chk(self._l.dymu_set_total_cost_export(self._h, out.ctypes.data_as(_dp), out.shape[1], xform,
+                                                     C.byref(direct)))
+        return bool(direct.value)
 
     def download_total_cost_end(self):
         self._chk(self._l.dymu_download_total_cost_end(self._h))

@@ -123,6 +123,11 @@ bool DyMuPathPlanner::initGlobalLayer(double globalres,
     // the local window is allocated up front (the reference builds its whole node graph here): the
     // first repair does not pay for cudaMalloc
     local_created = deviceOk(dymu_local_create(dev, local_window_nodes), "local window");
+    if (readback_target && readback_ld >= num_nodes_X)
+    {
+        int direct = 0;  // the matrix target outlives a re-initialisation
+        dymu_set_total_cost_export(dev, readback_target, readback_ld, DYMU_XFORM_INF_TO_MINUS1, &direct);
+    }
     return true;
 }
 
@@ -169,11 +174,21 @@ void DyMuPathPlanner::finishReadback()
 // (inf -> -1, G.cpp:799-811) is copied into `out` on the copy stream, overlapping whatever the
 // caller does next (getPath); getTotalCostMatrix(out, ld) with the same pointer then only waits for
 // that copy.  NULL switches it off.
+// When `out` is page-locked memory the device can write to (cudaHostAlloc / cudaHostRegister, a torch
+// pinned tensor), a solve from scratch stores the matrix there itself while it runs -- every tile as
+// soon as the wave front is past it (dymu_set_total_cost_export) -- and there is no copy left to wait
+// for.  `out` must stay valid until the target is changed or switched off.
 void DyMuPathPlanner::setTotalCostMatrixTarget(double* out, size_t ld)
 {
     finishReadback();
     readback_target = out;
     readback_ld = ld;
+    if (dev)
+    {
+        int direct = 0;
+        deviceOk(dymu_set_total_cost_export(dev, out, ld, DYMU_XFORM_INF_TO_MINUS1, &direct),
+                 "setTotalCostMatrixTarget");
+    }
 }
 
 void DyMuPathPlanner::startReadback()

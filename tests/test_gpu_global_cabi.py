@@ -255,3 +255,54 @@ def test_incremental_resolve_equals_full_solve(pkg):
     T, Tf = dev.download_total_cost(), ref.download_total_cost()
     fin = np.isfinite(Tf) & (Tf > 0)
     assert np.array_equal(np.isinf(T), np.isinf(Tf)) and np.max(np.abs(T[fin] - Tf[fin]) / Tf[fin]) <= 1e-13
+
+
+@pytest.mark.parametrize("ny,nx,streamed", [(777, 1000, False), (608, 352, True), (64, 64, False)])
+def test_direct_delivery_of_total_cost_matrix(pkg, ny, nx, streamed):
+    """dymu_set_total_cost_export: the solve kernel stores every tile of the total-cost matrix into
+    the caller's page-locked buffer once the front is past it.  What arrives is, bit for bit, what a
+    read-back of the plane gives afterwards (inf -> -1, G.cpp:799-811); columns beyond nx are not
+    touched; an unpinned buffer is declined and the ordinary read-back keeps working."""
+    import torch
+    api, syn = pkg.cuda_api, pkg.synthetic
+    dev = api.DeviceLayer(nx, ny)
+    cost = np.ascontiguousarray(syn.smooth_cost_map(ny, nx, seed=11))
+    dev.set_cost_map(cost)
+    ob = dev.download_plane_u8("obstacle")
+    goal = syn.free_interior_cell_near(ob, nx // 3, ny // 2)
+    ld = nx + 5
+    pinned = torch.full((ny, ld), float("nan"), dtype=torch.float64).pin_memory()
+    buf = pinned.numpy()
+    assert dev.set_total_cost_export(buf, xform=api.XFORM_INF_TO_MINUS1)
+    n_tiles = ((nx + 31) // 32) * ((ny + 31) // 32)
+    for rep in range(2):  # the second solve must not take anything of the first for delivered
+        buf[:] = np.nan
+        st = dev.plan_streamed(cost, goal) if streamed else dev.solve_total_cost([goal])
+        assert st["converged"]
+        assert st["tiles_delivered_early"] + st["tiles_delivered_late"] >= n_tiles
+        if nx * ny > 100000:
+            assert st["tiles_delivered_early"] > n_tiles // 2, st
+        # same pointer, ld and transform: nothing left to copy
+        dev.download_total_cost_begin(buf, xform=api.XFORM_INF_TO_MINUS1)
+        dev.download_total_cost_end()
+        want = np.empty((ny, nx))
+        dev.download_total_cost(out=want, xform=api.XFORM_INF_TO_MINUS1)
+        assert np.array_equal(buf[:, :nx], want)
+        assert np.isnan(buf[:, nx:]).all()
+    # a change to the plane ends the "already delivered" state: the copy happens again
+    dev.write_rect("total_cost", goal[0], goal[1], np.array([[123.0]]))
+    dev.download_total_cost_begin(buf, xform=api.XFORM_INF_TO_MINUS1)
+    dev.download_total_cost_end()
+    assert buf[goal[1], goal[0]] == 123.0 and np.isnan(buf[:, nx:]).all()
+    # switched off: solves leave the buffer alone
+    dev.set_total_cost_export(None)
+    buf[:] = np.nan
+    dev.solve_total_cost([goal])
+    assert np.isnan(buf).all()
+    # pageable memory is declined, not an error
+    plain = np.empty((ny, nx))
+    assert dev.set_total_cost_export(plain, xform=api.XFORM_INF_TO_MINUS1) is False
+    dev.solve_total_cost([goal])
+    dev.download_total_cost(out=plain, xform=api.XFORM_INF_TO_MINUS1)
+    # (two solves agree to rounding, not bit for bit)
+    assert np.array_equal(plain < 0, want < 0) and rel_err(plain, want) <= 1e-13
