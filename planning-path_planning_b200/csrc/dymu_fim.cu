@@ -116,6 +116,8 @@ struct Params
     uint32_t xnx, xny;          // logical size (the plane is padded to whole tiles)
     int xminus1;                // +inf is delivered as -1 (getTotalCostMatrix, G.cpp:799-811)
     uint32_t xcap;              // tiles one CTA delivers per phase at most (<= 64)
+    const uint32_t* stop_flag;  // leave after the phase in which *stop_flag >= stop_value (nullptr: never)
+    uint32_t stop_value;
 };
 constexpr unsigned long long kExported = 0xFFFFFFFFFFFFFFFFull;
 
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             converged = true;
             break;
         }
+        if (p.stop_flag && ld_volatile_u32(&p.ctrl[7])) break;  // asked to hand back (set before the last barrier)
 #ifdef DYMU_FIM_PROFILE
         if (tid == 0) { GT(tl_start) tl_fetch = tl_load = tl_sweep = tl_store = tl_start; tl_tiles = 0; }
 #endif
@@ -698,6 +701,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 #endif
         if (blockIdx.x == 0 && tid == 0)
         {
+            if (p.stop_flag && ld_volatile_u32(p.stop_flag) >= p.stop_value) p.ctrl[7] = 1;
             p.ctrl[old] = 0;      // count of the list that becomes "next" after this barrier
             p.ctrl[3 + old] = 0;  // and its cursor
             p.gmin[old] = kNoKey;
@@ -1098,6 +1102,8 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     }
     prm.ctrl = w->ctrl;
     prm.stats = w->stats;
+    prm.stop_flag = L.stop_flag;
+    prm.stop_value = L.stop_value;
     prm.tmax = nullptr;
     prm.xout = nullptr;
     prm.xld = 0;
@@ -1129,6 +1135,7 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     if (const char* e = getenv("DYMU_FIM_MAX_OUTER"))
         if (atoi(e) > 0) prm.max_outer = atoi(e);
     if (L.max_phases > 0) prm.max_outer = (int)L.max_phases;
+    const bool bounded = L.max_phases > 0 || L.stop_flag;
     prm.outer0 = w->rot;
     size_t total_tiles = (size_t)L.ntx * L.nty * L.nprob;
     w->unclean = true;  // until this launch reports that it drained its lists
@@ -1210,7 +1217,7 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
     w->rot = (int)((prm.outer0 + h[2]) % 3);
     w->pending = !h[3];
     w->unclean = !h[3];
-    if (!h[3] && L.max_phases == 0)
+    if (!h[3] && !bounded)
         DYMU_FAIL(ctx, DYMU_ERR_NOCONV, "tile FIM hit the outer-iteration cap (%d) before converging",
                   prm.max_outer);
     return DYMU_OK;
@@ -1318,6 +1325,11 @@ static int solve_total_cost_impl(dymu_ctx* ctx, uint32_t n_goals, const uint32_t
     L.seed_kind = 0; L.seed_data = (const uint32_t*)ctx->d_scratch;
     L.goal_obst = ctx->obst;
     L.max_phases = max_phases;
+    if (ctx->stream_stop_value)
+    {
+        L.stop_flag = ctx->d_upflag;
+        L.stop_value = ctx->stream_stop_value;
+    }
     ctx->export_done = false;
     if (ctx->export_dev && n_goals == 1)
     {
@@ -1432,8 +1444,14 @@ static int solve_resume_impl(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_r
     L.resume = keep_pending;
     L.max_phases = max_phases;
     L.seed_key = seed_key;
+    if (ctx->stream_stop_value)
+    {
+        L.stop_flag = ctx->d_upflag;
+        L.stop_value = ctx->stream_stop_value;
+    }
     // the tail of a streamed solve: the whole cost map is there now (tile bounds were tracked by the head)
-    L.track_final = L.export_now = deliver && ctx->export_dev && ctx->tile_tmax && max_phases == 0;
+    L.track_final = ctx->export_dev && ctx->tile_tmax;  // (values only drop: older bounds stay valid)
+    L.export_now = deliver && L.track_final && max_phases == 0;
     dymu_solve_stats local;
     memset(&local, 0, sizeof(local));
     rc = dymu_internal_fim_run(ctx, L, &local);
@@ -1463,11 +1481,19 @@ int dymu_set_cost_map_begin(dymu_ctx* ctx, const double* cost_host, size_t ld, u
     if (ctx->upload_pending) DYMU_TRY(dymu_internal_settle_upload(ctx));
     if (first_row >= ctx->ny) first_row = ctx->ny / 2;
     const uint32_t tile = ctx->tile, ny = ctx->ny;
-    // part A: the rows around `first_row`, uploaded first; part B: everything else
-    uint32_t reach = ny / 8 < 256 ? 256 : ny / 8;
-    uint32_t a0 = first_row > reach ? ((first_row - reach) / tile) * tile : 0;
-    uint32_t a1 = first_row + reach < ny ? dymu_div_up(first_row + reach, tile) * tile : ny;
-    if (a1 > ny) a1 = ny;
+    // Three parts, nearest first: a thin band of rows around `first_row` (the solve starts as soon
+    // as it is there), a wider band around it, everything else.  Behind the second and the third
+    // part the copy engine writes 1 / 2 into a device word the running solve kernel looks at.
+    auto band = [&](uint32_t reach, uint32_t& r0, uint32_t& r1) {
+        r0 = first_row > reach ? ((first_row - reach) / tile) * tile : 0;
+        r1 = first_row + reach < ny ? dymu_div_up(first_row + reach, tile) * tile : ny;
+        if (r1 > ny) r1 = ny;
+    };
+    uint32_t a0, a1, b0, b1;
+    band(4 * tile, a0, a1);
+    band(ny / 8 < 256 ? 256 : ny / 8, b0, b1);
+    if (b0 > a0) b0 = a0;
+    if (b1 < a1) b1 = a1;
     auto h2d_rows = [&](uint32_t j0, uint32_t j1) -> int {
         if (j0 >= j1) return DYMU_OK;
         DYMU_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->cost + (size_t)j0 * ctx->pitch, ctx->pitch * sizeof(double),
@@ -1476,86 +1502,136 @@ int dymu_set_cost_map_begin(dymu_ctx* ctx, const double* cost_host, size_t ld, u
                                              ctx->copy_stream));
         return DYMU_OK;
     };
+    auto flag = [&](uint32_t v) -> int {
+        DYMU_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_upflag, ctx->h_upvals + v, sizeof(uint32_t),
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        return DYMU_OK;
+    };
     // the copies must not overtake earlier work on the planes (a previous plan's read-back)
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up, ctx->stream));
     DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_up, 0));
+    DYMU_TRY(flag(0));
     DYMU_TRY(h2d_rows(a0, a1));
+    DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_part0, ctx->copy_stream));
+    DYMU_TRY(h2d_rows(b0, a0));
+    DYMU_TRY(h2d_rows(a1, b1));
+    DYMU_TRY(flag(1));
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_part, ctx->copy_stream));
-    DYMU_TRY(h2d_rows(0, a0));
-    DYMU_TRY(h2d_rows(a1, ny));
+    DYMU_TRY(h2d_rows(0, b0));
+    DYMU_TRY(h2d_rows(b1, ny));
+    DYMU_TRY(flag(2));
     DYMU_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up, ctx->copy_stream));
     ctx->upload_pending = true;
     ctx->up_a0 = a0;
     ctx->up_a1 = a1;
+    ctx->up_b0 = b0;
+    ctx->up_b1 = b1;
     ctx->solved = false;
     return DYMU_OK;
 }
 
-// The solve of a cost map whose upload (dymu_set_cost_map_begin) is still in flight: the rows
-// that have arrived are opened first, the rest stays impassable (C_eff = +inf) until it is there,
-// then the tiles along the two seams are woken again.
+// The solve of a cost map whose upload (dymu_set_cost_map_begin) is still in flight.  The rows that
+// have arrived are opened, the rest stays impassable (C_eff = +inf); the kernel hands back when the
+// copy engine reports the next part (or after `first_phases` phases when the caller fixes the cut),
+// that part is opened, the tiles along its seams are woken, and the solve goes on from its work lists.
 static int solve_streamed(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint32_t first_phases,
                           dymu_solve_stats* stats)
 {
-    if (first_phases == 0) first_phases = 40;
-    const uint32_t a0 = ctx->up_a0, a1 = ctx->up_a1, ny = ctx->ny;
+    const uint32_t a0 = ctx->up_a0, a1 = ctx->up_a1, b0 = ctx->up_b0, b1 = ctx->up_b1, ny = ctx->ny;
     ctx->upload_pending = false;
     // everything not uploaded yet is impassable for now
     DYMU_TRY(dymu_internal_fill(ctx, ctx->ceff, 1.0 / 0.0, (size_t)ctx->pitch * ctx->rows));
-    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_part, 0));
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_part0, 0));
     DYMU_TRY(dymu_internal_cost_rows(ctx, a0, a1));
     ctx->have_cost = true;
     ctx->ceff_dirty = false;
     // band width of the scheduler from the rows that are there (the mean cost of a Mars-like map
     // does not change much from one band of rows to the next)
     DYMU_TRY(dymu_internal_band_from_rows(ctx, a0, a1));
-    dymu_solve_stats first, rest;
-    memset(&first, 0, sizeof(first));
-    memset(&rest, 0, sizeof(rest));
-    int rc = solve_total_cost_impl(ctx, 1, &goal_i, &goal_j, first_phases, &first);
-    // the rest has arrived meanwhile: open it up and wake the tiles along the two seams
-    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
-    uint32_t ranges[4];
-    uint32_t n_ranges = 0;
-    if (a0 > 0)
+    dymu_solve_stats part[3];
+    memset(part, 0, sizeof(part));
+    // ---- part 1: until the second part is there
+    ctx->stream_stop_value = first_phases ? 0 : 1;
+    int rc = solve_total_cost_impl(ctx, 1, &goal_i, &goal_j, first_phases ? first_phases : (1u << 20), &part[0]);
+    ctx->stream_stop_value = 0;
+    auto open_rows = [&](uint32_t lo0, uint32_t lo1, uint32_t hi0, uint32_t hi1, uint32_t* ranges,
+                         uint32_t& n_ranges) -> int {
+        // rows [lo0, lo1) below and [hi0, hi1) above what is open: C_eff, and the seam rows to wake
+        n_ranges = 0;
+        if (lo1 > lo0)
+        {
+            DYMU_TRY(dymu_internal_cost_rows(ctx, lo0, lo1));
+            ranges[2 * n_ranges] = lo1 - 1;
+            ranges[2 * n_ranges + 1] = lo1 + 1;
+            n_ranges++;
+        }
+        if (hi1 > hi0)
+        {
+            DYMU_TRY(dymu_internal_cost_rows(ctx, hi0, hi1));
+            ranges[2 * n_ranges] = hi0 - 1;
+            ranges[2 * n_ranges + 1] = hi0 + 1;
+            n_ranges++;
+        }
+        return DYMU_OK;
+    };
+    uint32_t ranges[4], n_ranges = 0;
+    // ---- part 2: the wider band, until everything is there
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_part, 0));
+    DYMU_TRY(open_rows(b0, a0, a1, b1, ranges, n_ranges));
+    const bool seeded = rc == DYMU_OK && !part[0].goal_obstacle;
+    if (seeded && (n_ranges || !part[0].converged))
     {
-        DYMU_TRY(dymu_internal_cost_rows(ctx, 0, a0));
-        ranges[2 * n_ranges] = a0 - 1;
-        ranges[2 * n_ranges + 1] = a0 + 1;
-        n_ranges++;
+        const bool all_there = cudaEventQuery(ctx->ev_up) == cudaSuccess;
+        cudaGetLastError();  // (cudaErrorNotReady is an answer, not a failure)
+        if (!all_there || first_phases)
+        {
+            ctx->stream_stop_value = first_phases ? 0 : 2;
+            rc = solve_resume_impl(ctx, ranges, n_ranges, true, 0.0, first_phases ? 2 * first_phases : (1u << 20),
+                                   &part[1]);
+            ctx->stream_stop_value = 0;
+            n_ranges = 0;
+        }
     }
-    if (a1 < ny)
+    else
+        part[1].converged = part[0].converged;
+    // ---- part 3: the rest, to the end
+    DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
+    uint32_t ranges3[8], n3 = 0;
+    DYMU_TRY(open_rows(0, b0, b1, ny, ranges3, n3));
+    for (uint32_t k = 0; k < n_ranges; ++k)  // seams of part 2 that were not woken yet
     {
-        DYMU_TRY(dymu_internal_cost_rows(ctx, a1, ny));
-        ranges[2 * n_ranges] = a1 - 1;
-        ranges[2 * n_ranges + 1] = a1 + 1;
-        n_ranges++;
+        ranges3[2 * n3] = ranges[2 * k];
+        ranges3[2 * n3 + 1] = ranges[2 * k + 1];
+        n3++;
     }
     if (rc != DYMU_OK) return rc;
-    if (first.goal_obstacle)
+    if (part[0].goal_obstacle)
     {
         // nothing was seeded (G.cpp:447-451: "The goal is not valid"); the planes are complete
-        if (stats) *stats = first;
+        if (stats) *stats = part[0];
         ctx->solved = false;
         return DYMU_OK;
     }
-    if (n_ranges || !first.converged)
-        rc = solve_resume_impl(ctx, ranges, n_ranges, true, 0.0, 0, &rest, true);
+    if (n3 || ctx->work.pending)
+        rc = solve_resume_impl(ctx, ranges3, n3, true, 0.0, 0, &part[2], true);
     else
-        rest.converged = 1;
+        part[2].converged = 1;
     if (stats)
     {
-        *stats = first;
-        stats->outer_iterations += rest.outer_iterations;
-        stats->converged = rest.converged;
-        stats->tile_activations += rest.tile_activations;
-        stats->cell_updates += rest.cell_updates;
-        stats->tiles_deferred += rest.tiles_deferred;
-        stats->inner_iterations += rest.inner_iterations;
-        stats->cells_written += rest.cells_written;
-        stats->tiles_delivered_early = rest.tiles_delivered_early;
-        stats->tiles_delivered_late = rest.tiles_delivered_late;
-        stats->kernel_ms += rest.kernel_ms;
+        *stats = part[0];
+        for (int k = 1; k < 3; ++k)
+        {
+            stats->outer_iterations += part[k].outer_iterations;
+            stats->tile_activations += part[k].tile_activations;
+            stats->cell_updates += part[k].cell_updates;
+            stats->tiles_deferred += part[k].tiles_deferred;
+            stats->inner_iterations += part[k].inner_iterations;
+            stats->cells_written += part[k].cells_written;
+            stats->kernel_ms += part[k].kernel_ms;
+        }
+        stats->converged = part[2].converged;
+        stats->tiles_delivered_early = part[2].tiles_delivered_early;
+        stats->tiles_delivered_late = part[2].tiles_delivered_late;
     }
     ctx->solved = (rc == DYMU_OK);
     return rc;

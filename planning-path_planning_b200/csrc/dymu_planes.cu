@@ -423,6 +423,11 @@ int dymu_create(int device, uint32_t nx, uint32_t ny, double global_res, double 
     DYMU_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_part, cudaEventDisableTiming));
+    DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_part0, cudaEventDisableTiming));
+    DYMU_CUDA_TRY(ctx, cudaMalloc((void**)&ctx->d_upflag, 4 * sizeof(uint32_t)));
+    DYMU_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_upflag, 0, 4 * sizeof(uint32_t), ctx->stream));
+    DYMU_CUDA_TRY(ctx, cudaHostAlloc((void**)&ctx->h_upvals, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+    for (uint32_t k = 0; k < 4; ++k) ctx->h_upvals[k] = k;
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
     DYMU_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
@@ -463,7 +468,7 @@ int dymu_destroy(dymu_ctx* ctx)
     dymu_internal_fim_free(&ctx->work);
     void* ptrs[] = {ctx->elev, ctx->slope, ctx->raw, ctx->cost, ctx->haz, ctx->traff, ctx->ceff,
                     ctx->T, ctx->terrain, ctx->obst, ctx->locmode, ctx->d_lut, ctx->d_slopes,
-                    ctx->d_stage, ctx->d_scratch, ctx->tile_tmax};
+                    ctx->d_stage, ctx->d_scratch, ctx->tile_tmax, ctx->d_upflag};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -474,6 +479,8 @@ int dymu_destroy(dymu_ctx* ctx)
         if (ctx->user_ev[k]) cudaEventDestroy(ctx->user_ev[k]);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->ev_part) cudaEventDestroy(ctx->ev_part);
+    if (ctx->ev_part0) cudaEventDestroy(ctx->ev_part0);
+    if (ctx->h_upvals) cudaFreeHost(ctx->h_upvals);
     if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
     if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
