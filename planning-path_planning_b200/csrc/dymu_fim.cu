@@ -356,7 +356,15 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             converged = true;
             break;
         }
-        if (p.stop_flag && ld_volatile_u32(&p.ctrl[7])) break;  // asked to hand back (set before the last barrier)
+        if (p.stop_flag)
+        {
+            // Asked to hand back?  ctrl[7] holds the iteration BEFORE which every CTA leaves: CTA 0
+            // writes it ahead of its arrival at a barrier, and it may already be running one phase
+            // ahead of a CTA that is slow to leave that barrier -- a plain flag would make the slow
+            // one leave a phase early and the others wait for it forever.
+            const uint32_t stop_at = ld_volatile_u32(&p.ctrl[7]);
+            if (stop_at != 0 && stop_at <= (uint32_t)outer + 1u) break;
+        }
 #ifdef DYMU_FIM_PROFILE
         if (tid == 0) { GT(tl_start) tl_fetch = tl_load = tl_sweep = tl_store = tl_start; tl_tiles = 0; }
 #endif
@@ -701,7 +709,8 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
 #endif
         if (blockIdx.x == 0 && tid == 0)
         {
-            if (p.stop_flag && ld_volatile_u32(p.stop_flag) >= p.stop_value) p.ctrl[7] = 1;
+            if (p.stop_flag && ld_volatile_u32(&p.ctrl[7]) == 0 && ld_volatile_u32(p.stop_flag) >= p.stop_value)
+                p.ctrl[7] = (uint32_t)outer + 2u;  // = (next iteration) + 1, never 0
             p.ctrl[old] = 0;      // count of the list that becomes "next" after this barrier
             p.ctrl[3 + old] = 0;  // and its cursor
             p.gmin[old] = kNoKey;
@@ -712,11 +721,12 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
             // -- they would only wait -- look through the tile bounds (a share of the array each,
             // by order of arrival) and deliver the tiles the front has left behind.  The CTAs the
             // others are waiting for skip this, so a phase is not made longer.
+            // the smallest key that was pending when this phase began: every value below it is final.
+            // Read BEFORE arriving -- nothing writes gmin[cur] during its own phase, but once this CTA
+            // has arrived the others may run ahead and recycle that slot for the phase after next.
+            const unsigned long long gm = ld_volatile_u64(&p.gmin[cur]);
             grid_barrier_arrive(&p.ctrl[6], phase, &s_xorder);
             if (tid == 0) s_xn = 0;
-            // the smallest key that was pending when this phase began (nothing writes gmin[cur]
-            // during its own phase): every value below it is final
-            const unsigned long long gm = ld_volatile_u64(&p.gmin[cur]);
             __syncthreads();
             const uint32_t order = s_xorder, sharers = max(gridDim.x / 2u, 1u);
             if (order < sharers)
