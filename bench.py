@@ -858,16 +858,62 @@ def dd16384(args, D, pkg):
     return rec
 
 
+class Watchdog:
+    """A leg that does not come back (a deadlocked kernel, a rank that died inside a collective) must
+    not take the whole line with it: when a leg overruns its allowance, rank 0 prints the line as far
+    as it got, marked `incomplete`, and every rank leaves (ctypes calls release the GIL, so this
+    thread runs while the main thread is stuck in one)."""
+    ALLOWANCE = {"plan4096": 300.0, "config2_repair": 180.0, "queries2048": 420.0, "dd16384": 240.0}
+
+    def __init__(self, rank):
+        import threading
+        self.rank, self.leg, self.t0, self.line = rank, None, 0.0, None
+        self.lock = threading.Lock()
+        t = threading.Thread(target=self._run, daemon=True)
+        t.start()
+
+    def enter(self, leg):
+        with self.lock:
+            self.leg, self.t0 = leg, time.perf_counter()
+        print("[bench] rank %d: %s ..." % (self.rank, leg), file=sys.stderr, flush=True)
+
+    def leave(self):
+        with self.lock:
+            if self.leg:
+                print("[bench] rank %d: %s done in %.1f s" % (self.rank, self.leg, time.perf_counter() - self.t0),
+                      file=sys.stderr, flush=True)
+            self.leg = None
+
+    def _run(self):
+        while True:
+            time.sleep(1.0)
+            with self.lock:
+                leg, t0, line = self.leg, self.t0, self.line
+            if leg and time.perf_counter() - t0 > self.ALLOWANCE.get(leg, 300.0):
+                msg = "leg %s did not return within %.0f s on rank %d" % (leg, self.ALLOWANCE.get(leg, 300.0),
+                                                                           self.rank)
+                print("[bench] " + msg + ": giving up", file=sys.stderr, flush=True)
+                if self.rank == 0 and line is not None:
+                    line = dict(line)
+                    line["incomplete"] = msg
+                    print(json.dumps(line), flush=True)
+                    os._exit(0)
+                os._exit(0 if self.rank != 0 else 3)
+
+
 def run_b200(args):
     import dymu_b200
     D = Dist()
+    dog = Watchdog(D.rank)
     affinity = pin_rank(D.local_rank, D.world)
     pkg = dymu_b200.load()
     want = set(args.workload.split(",")) if args.workload != "all" else {"plan4096", "config2", "queries2048",
                                                                         "dd16384"}
     line, maps = None, None
     if "plan4096" in want:
+        dog.enter("plan4096")
         res = headline_plan4096(args, D, pkg, affinity)
+        dog.leave()
         if D.rank == 0:
             line, maps = res
             line["stencils"] = stencil_leg(args, D, pkg)
@@ -881,11 +927,15 @@ def run_b200(args):
         if key not in want:
             continue
         t0 = time.perf_counter()
+        if D.rank == 0 and line is not None:
+            dog.line = dict(line, **extra)
+        dog.enter(name)
         try:
             rec = fn(args, D, pkg)
         except Exception as e:  # a sub-benchmark must not take the headline line down with it
             rec = {"error": "%s: %s" % (type(e).__name__, e)}
         D.host_barrier("after_" + name)
+        dog.leave()
         if D.rank == 0 and rec is not None:
             rec["bench_seconds"] = time.perf_counter() - t0
             extra[name] = rec

@@ -140,9 +140,40 @@ __device__ __forceinline__ unsigned long long key_of(double v)
     return (unsigned long long)__double_as_longlong(v);
 }
 
+// Waits until *counter >= target.  A grid that lost a CTA (a defect, not a load condition) would
+// spin here for ever and take the GPU with it: after about eight seconds of waiting the CTA gives
+// up and says so in *abort_flag, which makes every other waiting CTA give up as well; the host
+// reports the solve as failed.
+// (not inlined: its loop state would otherwise take registers from the sweep)
+__device__ __noinline__ bool barrier_spin(const uint32_t* counter, uint32_t target,
+                                          unsigned long long* abort_flag)
+{
+    uint32_t polls = 0;
+    unsigned long long t0 = 0;
+    while (ld_volatile_u32(counter) < target)
+    {
+        if ((++polls & 0x3FFFu) == 0)
+        {
+            if (ld_volatile_u64(abort_flag)) return false;
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ull)
+            {
+                *abort_flag = 1ull;
+                __threadfence();
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
 // grid-wide barrier on a monotonically increasing arrival counter (all CTAs are
-// co-resident: the kernel is launched with cudaLaunchCooperativeKernel)
-__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& phase)
+// co-resident: the kernel is launched with cudaLaunchCooperativeKernel).  `ok` is a word in
+// shared memory; the return value (false: the grid is being abandoned) is the same for the whole CTA.
+__device__ __forceinline__ bool grid_barrier(uint32_t* counter, uint32_t& phase, unsigned long long* abort_flag,
+                                             uint32_t* ok)
 {
     __syncthreads();
     if (threadIdx.x == 0)
@@ -150,11 +181,12 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& phase)
         __threadfence();
         uint32_t target = (phase + 1) * gridDim.x;
         atomicAdd(counter, 1u);
-        while (ld_volatile_u32(counter) < target) { }
+        *ok = barrier_spin(counter, target, abort_flag) ? 1u : 0u;
         __threadfence();
     }
     phase++;
     __syncthreads();
+    return *ok != 0;
 }
 
 // the same barrier in two halves, so that a CTA can do work nobody waits for in between
@@ -167,16 +199,18 @@ __device__ __forceinline__ void grid_barrier_arrive(uint32_t* counter, uint32_t 
         *order = atomicAdd(counter, 1u) - phase * gridDim.x;  // how many CTAs arrived before this one
     }
 }
-__device__ __forceinline__ void grid_barrier_wait(uint32_t* counter, uint32_t& phase)
+__device__ __forceinline__ bool grid_barrier_wait(uint32_t* counter, uint32_t& phase, unsigned long long* abort_flag,
+                                                  uint32_t* ok)
 {
     if (threadIdx.x == 0)
     {
         uint32_t target = (phase + 1) * gridDim.x;
-        while (ld_volatile_u32(counter) < target) { }
+        *ok = barrier_spin(counter, target, abort_flag) ? 1u : 0u;
         __threadfence();
     }
     phase++;
     __syncthreads();
+    return *ok != 0;
 }
 
 template <int MODE> __device__ __forceinline__ double outside_value()
@@ -263,6 +297,7 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
     __shared__ uint32_t s_tmax;                // high word (rounded up) of the largest passable value
     __shared__ uint32_t s_xn, s_xlist[64];     // tiles this CTA delivers in the current phase
     __shared__ uint32_t s_xorder;              // its order of arrival at the barrier
+    __shared__ uint32_t s_bar_ok;              // grid barrier: 0 when the grid is being abandoned
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_per_prob = p.ntx * p.nty;
@@ -748,10 +783,10 @@ __global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS) k_fim
                 for (uint32_t q = 0; q < n; ++q) deliver_tile(s_xlist[q]);
                 if (tid == 0 && n) atomicAdd(&p.stats[7], (unsigned long long)n);
             }
-            grid_barrier_wait(&p.ctrl[6], phase);
+            if (!grid_barrier_wait(&p.ctrl[6], phase, &p.stats[14], &s_bar_ok)) break;
         }
-        else
-            grid_barrier(&p.ctrl[6], phase);
+        else if (!grid_barrier(&p.ctrl[6], phase, &p.stats[14], &s_bar_ok))
+            break;
         PC_MARK(pc_barrier)
     }
 #ifdef DYMU_FIM_PROFILE
@@ -1222,6 +1257,13 @@ int dymu_internal_fim_run(dymu_ctx* ctx, const dymu_fim_launch& L, dymu_solve_st
         const uint32_t nt_all = L.ntx * L.nty;
         stats->tiles_delivered_late = (prm.xout && h[3] && nt_all > h[7]) ? nt_all - (uint32_t)h[7] : 0;
         DYMU_CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev1, ctx->ev2));
+    }
+    if (h[14])
+    {
+        // a CTA waited eight seconds at the grid barrier and the grid gave up (see barrier_spin)
+        w->pending = false;
+        DYMU_FAIL(ctx, DYMU_ERR_CUDA, "tile FIM: the grid barrier timed out after %llu phases (solver defect); "
+                                      "the total-cost plane is not valid", h[2]);
     }
     if (prm.xout && h[3]) ctx->export_done = true;  // the tail ran: the caller's matrix is complete
     w->rot = (int)((prm.outer0 + h[2]) % 3);
