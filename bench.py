@@ -419,6 +419,22 @@ def headline_plan4096(args, D, pkg, affinity):
     start = syn.free_interior_cell_near(ob, n // 8, n // 8)
     tile, pitch, rows = dev.geometry()
 
+    retries = {"resident": 0, "cabi": 0, "class": 0}
+
+    def guarded(what, fn):
+        """A plan that fails (the solver reports its own defects, e.g. a grid barrier that timed out)
+        is logged, counted and run again inside the timed region, at most three times per arm: the
+        other ranks are waiting in a collective and must not be left there."""
+        try:
+            return fn()
+        except (RuntimeError, AssertionError) as e:
+            retries[what] += 1
+            print("[bench] rank %d: %s plan failed (%s), running it again" % (rank, what, e), file=sys.stderr,
+                  flush=True)
+            if retries[what] > 3:
+                raise
+            return fn()
+
     def plan():
         st = dev.solve_total_cost([goal])
         wps, status = dev.extract_global_path(float(start[0]), float(start[1]), 0.4, goal[0],
@@ -427,7 +443,7 @@ def headline_plan4096(args, D, pkg, affinity):
 
     # ---- resident-input arm -----------------------------------------------------------
     for _ in range(args.warmup):
-        st, nwp, status = plan()
+        st, nwp, status = guarded("resident", plan)
     reached = dev.count_reached()
     assert reached >= 0.90 * n * n, "goal is walled in: only %.3f of the map reached" % (
         reached / float(n * n))
@@ -439,7 +455,7 @@ def headline_plan4096(args, D, pkg, affinity):
     kernel_ms, tiles, updates, outers, written = [], [], [], [], []
     dev.event_record(0)
     for _ in range(args.steps):
-        st, nwp, status = plan()
+        st, nwp, status = guarded("resident", plan)
         kernel_ms.append(st["kernel_ms"])
         tiles.append(st["tile_activations"])
         updates.append(st["cell_updates"])
@@ -461,7 +477,6 @@ def headline_plan4096(args, D, pkg, affinity):
     # the matrix is page-locked: the solve kernel stores each tile into it as soon as the front
     # is past the tile (dymu_set_total_cost_export), download_*_begin/_end then have nothing to copy
     direct = dev.set_total_cost_export(t_host.numpy(), xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
-
     def plan_cabi():
         st_ = dev.plan_streamed(cost_host.numpy(), goal)
         dev.download_total_cost_begin(t_host.numpy(), xform=pkg.cuda_api.XFORM_INF_TO_MINUS1)
@@ -470,11 +485,11 @@ def headline_plan4096(args, D, pkg, affinity):
         return st_
 
     for _ in range(min(2, args.warmup)):
-        plan_cabi()
+        guarded("cabi", plan_cabi)
     D.barrier()
     dev.event_record(2)
     for _ in range(args.steps):
-        st_cabi = plan_cabi()
+        st_cabi = guarded("cabi", plan_cabi)
     dev.event_record(3)
     dev.set_total_cost_export(None)
     cabi_ms = dev.event_elapsed_ms(2, 3)
@@ -510,11 +525,11 @@ def headline_plan4096(args, D, pkg, affinity):
         return len(path)
 
     for _ in range(max(1, min(2, args.warmup))):
-        nwp_class = plan_class()
+        nwp_class = guarded("class", plan_class)
     D.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        nwp_class = plan_class()
+        nwp_class = guarded("class", plan_class)
     torch.cuda.synchronize()
     class_ms = (time.perf_counter() - t0) * 1e3
     D.barrier()
@@ -599,6 +614,7 @@ def headline_plan4096(args, D, pkg, affinity):
         "e2e": {"value": world * 1e3 / (class_ms / args.steps), "unit": UNIT,
                 "ms_per_step": class_ms / args.steps,
                 "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + nwp * 32,
+                "plans_run_again_after_a_solver_error": retries["class"],
                 "api": "DyMuPathPlanner::setCostMap(const double*, ld) -> computeEntireTotalCostMap() -> "
                        "getPath() -> getTotalCostMatrix(double*, ld) through libdymu_b200.so, pinned "
                        "host buffers (the cost map is uploaded while the solve starts, the matrix is stored "
@@ -606,6 +622,7 @@ def headline_plan4096(args, D, pkg, affinity):
                        "over ranks)"},
         "e2e_cabi": {"value": world * 1e3 / (cabi_ms / args.steps), "unit": UNIT,
                      "ms_per_step": cabi_ms / args.steps,
+                     "plans_run_again_after_a_solver_error": retries["cabi"],
                      "api": "dymu_set_total_cost_export + dymu_plan_streamed + dymu_download_total_cost_begin/"
                             "_end + dymu_extract_global_path (include/dymu_cuda.h), CUDA events",
                      "matrix_delivery": {"direct": bool(direct),
@@ -614,6 +631,7 @@ def headline_plan4096(args, D, pkg, affinity):
                                          "solve_kernel_ms": st_cabi["kernel_ms"]}},
         "link_gbs_per_rank": [{"h2d": r[0], "d2h": r[1]} for r in rates],
         "gpu_launches": int(launches),
+        "plans_run_again_after_a_solver_error": retries["resident"],
         "clocks": clocks,
     }
     return line, (elev, terr, lut, slopes, locs)
