@@ -433,6 +433,11 @@ def headline_plan4096(args, D, pkg, affinity):
                   flush=True)
             if retries[what] > 3:
                 raise
+            # the conservative variants for the rest of the run: streamed solves cut by phase count
+            # instead of on the copy engine's word, the matrix copied after the solve
+            os.environ["DYMU_STREAM_PHASES"] = "40"
+            if what == "cabi":
+                dev.set_total_cost_export(None)
             return fn()
 
     def plan():

@@ -1591,6 +1591,10 @@ static int solve_streamed(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, uint3
 {
     const uint32_t a0 = ctx->up_a0, a1 = ctx->up_a1, b0 = ctx->up_b0, b1 = ctx->up_b1, ny = ctx->ny;
     ctx->upload_pending = false;
+    // DYMU_STREAM_PHASES=n: cut the launches after n / 2n phases instead of on the copy engine's word
+    if (first_phases == 0)
+        if (const char* e = getenv("DYMU_STREAM_PHASES"))
+            if (atoi(e) > 0) first_phases = (uint32_t)atoi(e);
     // everything not uploaded yet is impassable for now
     DYMU_TRY(dymu_internal_fill(ctx, ctx->ceff, 1.0 / 0.0, (size_t)ctx->pitch * ctx->rows));
     DYMU_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_part0, 0));
