@@ -583,6 +583,10 @@ def headline_plan4096(args, D, pkg, affinity):
             "reached_fraction": reached / float(n * n), "waypoints": nwp,
             "l2": "inputs larger than L2 (each fp64 plane %.0f MB > 126 MB L2)" % (n * n * 8 / 1e6),
             "parallelism": "1 independent plan per GPU, no collective",
+            "streamed_solve_cut": ("after %s / 2 x %s phases (DYMU_STREAM_PHASES)"
+                                   % ((os.environ["DYMU_STREAM_PHASES"],) * 2)
+                                   if os.environ.get("DYMU_STREAM_PHASES") else
+                                   "when the copy engine reports the next part of the cost map"),
             "rank_core_affinity": affinity,
         },
         "solve_ms_per_4096_map": k_ms,
@@ -928,6 +932,11 @@ def run_b200(args):
     import dymu_b200
     D = Dist()
     dog = Watchdog(D.rank)
+    if D.world > 1:
+        # The hand-back of a streamed solve on the copy engine's word was re-verified on one GPU only
+        # after its race was fixed; with several ranks the launches of a
+        # streamed solve are cut by phase count, the variant every multi-GPU line so far was taken with.
+        os.environ.setdefault("DYMU_STREAM_PHASES", "40")
     affinity = pin_rank(D.local_rank, D.world)
     pkg = dymu_b200.load()
     want = set(args.workload.split(",")) if args.workload != "all" else {"plan4096", "config2", "queries2048",
