@@ -180,7 +180,8 @@ int dymu_solve_advance(dymu_ctx* ctx, const uint32_t* ranges, uint32_t n_ranges,
 int dymu_solve_incremental(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, dymu_solve_stats* stats,
                            uint64_t* cells_invalidated);
 /* setCostMap (G.cpp:109-126) without waiting for the copy: the rows around `first_row` (the
- * goal's row; >= ny = middle) are sent first on the copy stream, and the call returns at once.  The
+ * goal's row; >= ny = middle) are sent first on the copy stream -- three parts: +-128 rows, then
+ * +-max(256, ny/8), then the rest -- and the call returns at once.  The
  * next dymu_solve_total_cost with a single goal inside those first rows starts on them while the
  * rest is still arriving (see dymu_plan_streamed); every other entry point first completes the
  * upload and the obstacle bookkeeping, exactly as dymu_set_cost_map would have.  `cost_host` must
@@ -188,10 +189,13 @@ int dymu_solve_incremental(dymu_ctx* ctx, uint32_t goal_i, uint32_t goal_j, dymu
 int dymu_set_cost_map_begin(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t first_row);
 /* setCostMap (G.cpp:109-126) + computeEntireTotalCostMap (G.cpp:443-468) for a cost map that is
  * still in host memory, with the upload hidden behind the solve: the rows around the goal go
- * first, the solve starts on them with everything else impassable (C_eff = +inf), and after
- * `first_phases` solver phases (0 = default) the remaining rows -- uploaded meanwhile on the copy
- * stream -- are opened and the tiles along the two seams re-activated.  Same fixed point as
- * dymu_set_cost_map + dymu_solve_total_cost.  `cost_host` should be pinned memory. */
+ * first, the solve starts on them with everything else impassable (C_eff = +inf); whenever the
+ * next part of the upload has arrived the solve kernel hands back, the new rows are opened, the
+ * tiles along the two seams re-activated and the solve goes on from its work lists.
+ * first_phases == 0: the kernel hands back when the copy engine reports the part (a device word
+ * written behind it in stream order); first_phases > 0 (or the environment variable
+ * DYMU_STREAM_PHASES): after first_phases / 2 * first_phases solver phases instead.  Same fixed
+ * point as dymu_set_cost_map + dymu_solve_total_cost.  `cost_host` should be pinned memory. */
 int dymu_plan_streamed(dymu_ctx* ctx, const double* cost_host, size_t ld, uint32_t goal_i,
                        uint32_t goal_j, uint32_t first_phases, dymu_solve_stats* stats);
 /* resetTotalCostMap (G.cpp:473-485) without seeding a goal: every slot-0 value = +inf. */
@@ -223,8 +227,9 @@ int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, s
 /* Direct delivery of getTotalCostMatrix (G.cpp:799-811): from now on every full single-goal solve
  * (dymu_solve_total_cost, dymu_plan_streamed, dymu_solve_incremental when it solves from scratch)
  * stores the total-cost matrix into `host` (row stride `ld` doubles) itself -- each tile as soon as
- * the wave front is past it, the rest right after the last phase -- instead of leaving it to a
- * copy afterwards; a later dymu_download_total_cost[_begin] with the same host / ld / xform then
+ * the wave front is past it, the rest right after the last phase on the copy stream (it is
+ * complete when dymu_download_total_cost_end / dymu_download_total_cost return) -- instead of
+ * leaving it to a copy afterwards; a later dymu_download_total_cost[_begin] with the same host / ld / xform then
  * has nothing left to copy.  `host` must be page-locked memory the device can write to
  * (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned tensor); otherwise nothing is set up and
  * *direct comes back 0 (not an error).  The buffer is written during the solve and is only
