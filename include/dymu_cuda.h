@@ -228,7 +228,7 @@ int dymu_download_total_cost_begin(dymu_ctx* ctx, uint32_t slot, double* host, s
  * (dymu_solve_total_cost, dymu_plan_streamed, dymu_solve_incremental when it solves from scratch)
  * stores the total-cost matrix into `host` (row stride `ld` doubles) itself -- each tile as soon as
  * the wave front is past it, the rest right after the last phase on the copy stream (it is
- * complete when dymu_download_total_cost_end / dymu_download_total_cost return) -- instead of
+ * complete when dymu_download_total_cost_end, dymu_download_total_cost or dymu_synchronize return) -- instead of
  * leaving it to a copy afterwards; a later dymu_download_total_cost[_begin] with the same host / ld / xform then
  * has nothing left to copy.  `host` must be page-locked memory the device can write to
  * (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned tensor); otherwise nothing is set up and

@@ -498,6 +498,8 @@ int dymu_synchronize(dymu_ctx* ctx)
     DYMU_GUARD(ctx);
     if (!ctx) return DYMU_ERR_ARG;
     DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // ... and the rest of a direct matrix delivery, which runs on the copy stream
+    if (ctx->export_tail_pending) DYMU_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return DYMU_OK;
 }
 
