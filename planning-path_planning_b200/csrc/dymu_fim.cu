@@ -37,8 +37,14 @@
 // Environment switches (read once per context): DYMU_FIM_BAND (band width factor, default
 // 4), DYMU_FIM_INNER (sweep cap per activation, default 64), DYMU_FIM_BUDGET /
 // DYMU_FIM_MIN_SLICE (per-CTA sweep budget per phase, default off), DYMU_FIM_GRID_PER_SM,
-// DYMU_FIM_MAX_OUTER, DYMU_FIM_TRACE (per-phase timeline); build-time: -DDYMU_FIM_PROFILE
+// DYMU_FIM_MAX_OUTER, DYMU_FIM_TRACE (per-phase timeline); read per call: DYMU_STREAM_PHASES
+// (streamed solves cut after n / 2n phases instead of on the copy engine's word), DYMU_EXPORT_CAP
+// (tiles a CTA delivers per phase, default 1); build-time: -DDYMU_FIM_PROFILE
 // (clock64 section profile + DYMU_FIM_CTA_TRACE), -DDYMU_FIM_WARPS=8.
+// Direct delivery (dymu_set_total_cost_export): the kernel tracks an upper bound per tile and
+// stores a tile into the caller's page-locked matrix once that bound is below every pending key
+// (see Params::tmax); k_deliver_rest stores what is left.  A waiting CTA gives up after eight
+// seconds at the grid barrier (barrier_spin) and the solve returns an error instead of hanging.
 // The same kernel runs the local layer's risk dilation (propagateRisk,
 // src/DyMu_LocalPathRepairing.cpp:550-576) in MODE 1, a max-propagation on risk.
 #include <cooperative_groups.h>
